@@ -1,0 +1,176 @@
+"""ctypes binding of the CPU ORACLE (oracle/pmc_oracle.c).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Never imported by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+SENTINEL = np.float32(1.0e18)
+
+
+class Geom(C.Structure):
+    _fields_ = [
+        ("n_particles", C.c_int64), ("cps", C.c_int), ("n_cells", C.c_int64),
+        ("nmax", C.c_int), ("n_M", C.c_int), ("w", C.c_float), ("L", C.c_float),
+        ("half_L", C.c_float), ("sigma", C.c_float), ("sigma2", C.c_float),
+        ("delta", C.c_float), ("dscale", C.c_float), ("L_box", C.c_double),
+        ("seed", C.c_uint64),
+    ]
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "pmc_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        fp, sp = C.POINTER(C.c_float), C.POINTER(C.c_int16)
+        gp, u64p = C.POINTER(Geom), C.POINTER(C.c_uint64)
+        _lib.oracle_make_geom.argtypes = [C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int,
+                                          C.c_int, C.c_float, C.c_uint64, C.c_int, gp]
+        _lib.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        _lib.oracle_init_r.argtypes = [gp, fp]
+        _lib.oracle_assign.argtypes = [gp, fp, fp, sp]
+        _lib.oracle_assign.restype = C.c_int64
+        _lib.oracle_cell_of.argtypes = [gp, C.c_float]
+        _lib.oracle_subsweep.argtypes = [gp, fp, sp, C.POINTER(C.c_int), C.c_uint64, u64p, u64p]
+        _lib.oracle_shift_cells.argtypes = [gp, fp, sp, C.c_int, C.c_float]
+        _lib.oracle_shift_cells.restype = C.c_int64
+        _lib.oracle_schedule.argtypes = [gp, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), fp]
+        _lib.oracle_colour_to_off.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        _lib.oracle_sweep.argtypes = [gp, fp, sp, C.c_uint64, C.c_int, u64p, u64p]
+        _lib.oracle_sweep.restype = C.c_int64
+        _lib.oracle_sweep_omp.argtypes = [gp, fp, sp, C.c_uint64, C.c_int, u64p, u64p,
+                                          C.POINTER(C.c_int64)]
+        _lib.oracle_disk_to_r.argtypes = [gp, fp, sp, fp]
+        _lib.oracle_disk_to_r.restype = C.c_int64
+        _lib.oracle_check.argtypes = [gp, fp, sp, C.POINTER(C.c_int64), fp]
+        _lib.oracle_gr_hist.argtypes = [gp, fp, sp, C.c_float, C.c_int, u64p]
+    return _lib
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _s(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int16))
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().oracle_philox4x32_10(c, k, o)
+    return [int(x) for x in o]
+
+
+class Oracle:
+    """Host-side mirror of the C-ABI handle (include/pmc.h) on top of the C oracle."""
+
+    def __init__(self, n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4,
+                 move_delta=0.1, seed=1234, cps_multiple=2):
+        self.g = Geom()
+        rc = lib().oracle_make_geom(n_particles, phi, sigma_d, cell_w, nmax, n_M, move_delta,
+                                    seed, cps_multiple, C.byref(self.g))
+        if rc:
+            raise ValueError(f"oracle_make_geom failed rc={rc}")
+        self.trials = C.c_uint64(0)
+        self.accepted = C.c_uint64(0)
+        self.lost = 0
+
+    # geometry ---------------------------------------------------------------
+    @property
+    def n_cells(self):
+        return int(self.g.n_cells)
+
+    @property
+    def cps(self):
+        return int(self.g.cps)
+
+    def alloc(self):
+        disk = np.zeros((self.n_cells, 2, self.g.nmax), dtype=np.float32)
+        n = np.zeros(self.n_cells, dtype=np.int16)
+        return disk, n
+
+    # path -------------------------------------------------------------------
+    def init_r(self):
+        r = np.zeros((2, self.g.n_particles), dtype=np.float32)
+        if lib().oracle_init_r(C.byref(self.g), _f(r)):
+            raise ValueError("n_particles is not a perfect square")
+        return r
+
+    def assign(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float32)
+        disk, n = self.alloc()
+        self.lost += lib().oracle_assign(C.byref(self.g), _f(r), _f(disk), _s(n))
+        return disk, n
+
+    def cell_of(self, x):
+        return lib().oracle_cell_of(C.byref(self.g), C.c_float(x))
+
+    def subsweep(self, disk, n, off, sweep):
+        o = (C.c_int * 2)(*off)
+        lib().oracle_subsweep(C.byref(self.g), _f(disk), _s(n), o, sweep,
+                              C.byref(self.trials), C.byref(self.accepted))
+
+    def shift_cells(self, disk, n, f, d):
+        self.lost += lib().oracle_shift_cells(C.byref(self.g), _f(disk), _s(n), f, C.c_float(d))
+
+    def schedule(self, sweep):
+        order = (C.c_int * 4)()
+        f = C.c_int()
+        d = C.c_float()
+        lib().oracle_schedule(C.byref(self.g), sweep, order, C.byref(f), C.byref(d))
+        return list(order), f.value, np.float32(d.value)
+
+    @staticmethod
+    def colour_to_off(colour):
+        o = (C.c_int * 2)()
+        lib().oracle_colour_to_off(colour, o)
+        return [o[0], o[1]]
+
+    def sweep(self, disk, n, sweep0, n_sweeps, omp=False):
+        if omp:
+            lost = C.c_int64(0)
+            threads = lib().oracle_sweep_omp(C.byref(self.g), _f(disk), _s(n), sweep0, n_sweeps,
+                                             C.byref(self.trials), C.byref(self.accepted),
+                                             C.byref(lost))
+            self.lost += lost.value
+            return threads
+        self.lost += lib().oracle_sweep(C.byref(self.g), _f(disk), _s(n), sweep0, n_sweeps,
+                                        C.byref(self.trials), C.byref(self.accepted))
+        return 1
+
+    def disk_to_r(self, disk, n):
+        r = np.zeros((2, self.g.n_particles), dtype=np.float32)
+        k = lib().oracle_disk_to_r(C.byref(self.g), _f(disk), _s(n), _f(r))
+        return r, int(k)
+
+    def check(self, disk, n):
+        out = (C.c_int64 * 4)()
+        md2 = C.c_float()
+        lib().oracle_check(C.byref(self.g), _f(disk), _s(n), out, C.byref(md2))
+        return {"total": out[0], "out_of_cell": out[1], "overlaps": out[2],
+                "bad_sentinels": out[3], "min_d2": np.float32(md2.value)}
+
+    def gr_hist(self, disk, n, r_max, nbins):
+        h = np.zeros(nbins, dtype=np.uint64)
+        lib().oracle_gr_hist(C.byref(self.g), _f(disk), _s(n), C.c_float(r_max), nbins,
+                             h.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return h

@@ -1,0 +1,559 @@
+// pmc_api.cu -- the C-ABI (include/pmc.h): handle, geometry, host-side per-sweep randomness,
+// the sweep protocol of start.cu:237-260, observables glue, host I/O and the NCCL slab ring.
+#include "pmc_internal.cuh"
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ------------------------------------------------------------------ minimal NCCL surface
+// libnccl.so.2 (the copy torch ships) is dlopen'ed on first use so that single-GPU users
+// need no NCCL at all.  Declarations restated from nccl.h 2.27 (public API, stable ABI).
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt8 = 0 };
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load()
+{
+    if (g_nccl.lib) return true;
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    void *lib = nullptr;
+    for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) {
+        const char *env = getenv("PMC_NCCL_LIB");
+        if (env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!lib) return false;
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    g_nccl.Send = (decltype(g_nccl.Send))dlsym(lib, "ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))dlsym(lib, "ncclRecv");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(lib, "ncclGroupEnd");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv ||
+        !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.CommDestroy) { dlclose(lib); return false; }
+    g_nccl.lib = lib;
+    return true;
+}
+
+// ------------------------------------------------------------------ handle
+constexpr int kGhostRows = 5;   // fused sweep halo (4) + 1 upstream row of the pending shift
+
+struct pmc_handle {
+    pmc_params p;
+    pmc_geometry pg;
+    DevGeom g;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int blocking;
+    Counters *d_ctr;
+    float4 *scratch_disk;
+    int16_t *scratch_n;
+    long long *d_out4;
+    unsigned *d_min;
+    unsigned long long *d_hist;
+    int hist_cap;
+    // pmc_run_host buffers
+    float *run_r;
+    float4 *run_disk;
+    int16_t *run_n;
+    // slab ring
+    ncclComm_t comm;
+};
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+static int finish(pmc_handle *h)
+{
+    if (h->blocking) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static void host_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t out[4])
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+extern "C" {
+
+const char *pmc_error_string(int code)
+{
+    switch (code) {
+    case 0: return "success";
+    case PMC_E_INVALID: return "pmc: invalid argument";
+    case PMC_E_UNSUPPORTED: return "pmc: unsupported parameter (this build: nmax == 8)";
+    case PMC_E_OVERFLOW: return "pmc: a cell exceeded nmax particles";
+    case PMC_E_LOST: return "pmc: particles outside the box were dropped";
+    case PMC_E_NOT_SQUARE: return "pmc: init_r needs a perfect-square particle count";
+    case PMC_E_COMM: return "pmc: communicator error";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pmc: unknown error";
+    }
+}
+
+int pmc_create(const pmc_params *pp, pmc_handle **out)
+{
+    if (!pp || !out) return PMC_E_INVALID;
+    pmc_params p = *pp;
+    if (p.n_particles <= 0 || !(p.phi > 0.0f) || !(p.sigma_d > 0.0f) || !(p.cell_w >= p.sigma_d) ||
+        p.n_M < 1 || p.n_M > 64 || !(p.move_delta > 0.0f)) return PMC_E_INVALID;
+    if (p.nmax != PMC_NMAX) return PMC_E_UNSUPPORTED;
+    if (p.cps_multiple < 2) p.cps_multiple = 2;
+    if (p.cps_multiple & 1) return PMC_E_INVALID;
+    if (p.n_ranks < 1) p.n_ranks = 1;
+    if (p.rank < 0 || p.rank >= p.n_ranks) return PMC_E_INVALID;
+
+    // start.cu:14-27 as runtime values; identical arithmetic to oracle_make_geom
+    double L_d = sqrt((double)p.n_particles * M_PI * (double)p.sigma_d * (double)p.sigma_d / (4.0 * (double)p.phi));
+    long long cps = (long long)floor(L_d / ((double)p.cps_multiple * (double)p.cell_w)) * p.cps_multiple;
+    if (cps < 4 || cps > 46340) return PMC_E_INVALID;
+    double w_d = L_d / (double)cps;
+
+    pmc_handle *h = (pmc_handle *)calloc(1, sizeof(pmc_handle));
+    if (!h) return PMC_E_INVALID;
+    h->p = p;
+    DevGeom &g = h->g;
+    g.cps = (int)cps;
+    g.w = (float)w_d;
+    g.L_box = (double)cps * (double)g.w;
+    g.L = (float)g.L_box;
+    g.half_L = g.L / 2.0f;
+    g.sigma = p.sigma_d;
+    g.sigma2 = p.sigma_d * p.sigma_d;
+    g.dscale = p.move_delta * 5.9604644775390625e-08f;
+    g.n_M = p.n_M;
+    g.seed_lo = (unsigned)p.seed;
+    g.seed_hi = (unsigned)(p.seed >> 32);
+    g.n_particles = p.n_particles;
+    if (p.n_ranks == 1) {
+        g.row0 = 0; g.rows = g.cps; g.ghost = 0; g.wrap_y = 1;
+    } else {
+        // 1-D slabs of whole cell rows, even row count per slab so colours stay aligned
+        if (g.cps % (2 * p.n_ranks) != 0) { free(h); return PMC_E_INVALID; }
+        g.rows = g.cps / p.n_ranks;
+        g.row0 = p.rank * g.rows;
+        g.ghost = kGhostRows;
+        g.wrap_y = 0;
+        if (g.rows < 2 * kGhostRows) { free(h); return PMC_E_INVALID; }
+    }
+    g.local_rows = g.rows + 2 * g.ghost;
+
+    pmc_geometry &pg = h->pg;
+    pg.n_particles = p.n_particles; pg.cps = g.cps; pg.n_cells = cps * cps; pg.nmax = PMC_NMAX;
+    pg.n_M = p.n_M; pg.w = g.w; pg.L = g.L; pg.sigma_d = p.sigma_d; pg.move_delta = p.move_delta;
+    pg.row0 = g.row0; pg.rows = g.rows; pg.ghost_rows = g.ghost;
+    pg.local_cells = (long long)g.local_rows * g.cps;
+
+    if (p.device >= 0) { cudaError_t e = cudaSetDevice(p.device); if (e != cudaSuccess) { free(h); return (int)e; } }
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e != cudaSuccess) { free(h); return (int)e; }
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { free(h); return (int)e; }
+    h->own_stream = true;
+    h->blocking = 1;
+    e = cudaMalloc(&h->d_ctr, sizeof(Counters));
+    if (e == cudaSuccess) e = cudaMemset(h->d_ctr, 0, sizeof(Counters));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_out4, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_min, sizeof(unsigned));
+    if (e != cudaSuccess) { pmc_destroy(h); return (int)e; }
+    *out = h;
+    return 0;
+}
+
+int pmc_destroy(pmc_handle *h)
+{
+    if (!h) return PMC_E_INVALID;
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->d_ctr); cudaFree(h->scratch_disk); cudaFree(h->scratch_n);
+    cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
+    cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    free(h);
+    return 0;
+}
+
+int pmc_get_geometry(const pmc_handle *h, pmc_geometry *g)
+{
+    if (!h || !g) return PMC_E_INVALID;
+    *g = h->pg;
+    return 0;
+}
+
+size_t pmc_r_bytes(const pmc_handle *h) { return h ? (size_t)h->p.n_particles * 2 * sizeof(float) : 0; }
+size_t pmc_disk_bytes(const pmc_handle *h) { return h ? (size_t)h->pg.local_cells * 2 * PMC_NMAX * sizeof(float) : 0; }
+size_t pmc_n_bytes(const pmc_handle *h) { return h ? (size_t)h->pg.local_cells * sizeof(int16_t) : 0; }
+
+int pmc_set_stream(pmc_handle *h, void *cuda_stream)
+{
+    if (!h) return PMC_E_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int pmc_set_blocking(pmc_handle *h, int blocking)
+{
+    if (!h) return PMC_E_INVALID;
+    h->blocking = blocking ? 1 : 0;
+    return 0;
+}
+
+int pmc_synchronize(pmc_handle *h)
+{
+    if (!h) return PMC_E_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ the four call sites
+int pmc_init_r(pmc_handle *h, float *d_r)
+{
+    if (!h || !d_r) return PMC_E_INVALID;
+    long long N = h->p.n_particles;
+    long long ns = (long long)floor(sqrt((double)N) + 0.5);
+    if (ns * ns != N) return PMC_E_NOT_SQUARE;
+    CK(pmc_launch_init_r(h->g, d_r, h->stream));
+    return finish(h);
+}
+
+int pmc_assign(pmc_handle *h, const float *d_r, float *d_disk, int16_t *d_n)
+{
+    if (!h || !d_r || !d_disk || !d_n) return PMC_E_INVALID;
+    CK(pmc_launch_assign(h->g, d_r, (float4 *)d_disk, d_n, h->d_ctr, h->stream));
+    return finish(h);
+}
+
+void pmc_colour_to_off(int colour, int off[2])
+{
+    off[1] = colour % 2;            // itoa start.cu:153-157, two bits in 2-D
+    off[0] = (colour / 2) % 2;
+}
+
+int pmc_schedule(const pmc_handle *h, uint64_t sweep, int order[4], int *f, float *d)
+{
+    if (!h || !order || !f || !d) return PMC_E_INVALID;
+    uint32_t a[4], b[4];
+    host_philox(0xFFFFFFFFu, (uint32_t)sweep, (uint32_t)(sweep >> 32), (1u << 16) | 0u, h->p.seed, a);
+    host_philox(0xFFFFFFFFu, (uint32_t)sweep, (uint32_t)(sweep >> 32), (1u << 16) | 1u, h->p.seed, b);
+    for (int i = 0; i < 4; i++) order[i] = i;
+    for (int i = 3; i >= 1; i--) {                      // FY_Shuffle start.cu:34-44, unbiased
+        int j = (int)(((uint64_t)a[3 - i] * (uint64_t)(i + 1)) >> 32);
+        int t = order[i]; order[i] = order[j]; order[j] = t;
+    }
+    *f = (int)(a[3] >> 31);                             // kernel.cu:683 range, 2 axes
+    volatile float u = (float)((b[0] >> 8) + 1u) * 5.9604644775390625e-08f;
+    volatile float um = u - 0.5f;
+    *d = um * h->g.w;                                   // kernel.cu:684: (-w/2, w/2]
+    return 0;
+}
+
+static int ensure_scratch(pmc_handle *h)
+{
+    if (!h->scratch_disk) CK(cudaMalloc(&h->scratch_disk, pmc_disk_bytes(h)));
+    if (!h->scratch_n) CK(cudaMalloc(&h->scratch_n, pmc_n_bytes(h)));
+    return 0;
+}
+
+static int exchange_ghosts_async(pmc_handle *h, float4 *disk, int16_t *n)
+{
+    if (h->p.n_ranks <= 1) return 0;
+    if (!h->comm) return PMC_E_COMM;
+    const DevGeom &g = h->g;
+    const int G = g.ghost, R = h->p.n_ranks;
+    const int lower = (h->p.rank + R - 1) % R, upper = (h->p.rank + 1) % R;
+    const size_t drow = (size_t)g.cps * 64, nrow = (size_t)g.cps * sizeof(int16_t);
+    char *D = (char *)disk, *N = (char *)n;
+    // owned rows are local rows [G, G+rows)
+    int rc = 0;
+    rc |= g_nccl.GroupStart();
+    rc |= g_nccl.Send(D + (size_t)G * drow, G * drow, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.Send(D + (size_t)g.rows * drow, G * drow, ncclInt8, upper, h->comm, h->stream);
+    rc |= g_nccl.Recv(D + (size_t)(G + g.rows) * drow, G * drow, ncclInt8, upper, h->comm, h->stream);
+    rc |= g_nccl.Recv(D, G * drow, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.Send(N + (size_t)G * nrow, G * nrow, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.Send(N + (size_t)g.rows * nrow, G * nrow, ncclInt8, upper, h->comm, h->stream);
+    rc |= g_nccl.Recv(N + (size_t)(G + g.rows) * nrow, G * nrow, ncclInt8, upper, h->comm, h->stream);
+    rc |= g_nccl.Recv(N, G * nrow, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.GroupEnd();
+    return rc ? PMC_E_COMM : 0;
+}
+
+int pmc_subsweep(pmc_handle *h, float *d_disk, int16_t *d_n, const int off[2], uint64_t sweep)
+{
+    if (!h || !d_disk || !d_n || !off) return PMC_E_INVALID;
+    if ((off[0] | off[1]) & ~1) return PMC_E_INVALID;
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.offx[0] = off[0]; a.offy[0] = off[1];
+    a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
+    CK(pmc_launch_subsweep(h->g, (float4 *)d_disk, d_n, a, h->d_ctr, h->stream));
+    int rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
+    if (rc) return rc;
+    return finish(h);
+}
+
+int pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
+{
+    if (!h || !d_disk || !d_n || f < 0 || f > 1) return PMC_E_INVALID;
+    if (!(fabsf(d) <= 0.5f * h->g.w * 1.0001f)) return PMC_E_INVALID;   // shiftCells.h:7 contract
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    CK(pmc_launch_shift(h->g, (const float4 *)d_disk, d_n, h->scratch_disk, h->scratch_n, f, d, h->d_ctr, h->stream));
+    CK(cudaMemcpyAsync(d_disk, h->scratch_disk, pmc_disk_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_n, h->scratch_n, pmc_n_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+    rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
+    if (rc) return rc;
+    return finish(h);
+}
+
+// start.cu:237-260, n_sweeps times.  Sweep t runs as ONE kernel that first applies the shift
+// drawn at the end of sweep t-1 (while staging its tile) and then the four colours; the last
+// shift is materialised by the stand-alone kernel so the caller's arrays are complete.
+int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n_sweeps)
+{
+    if (!h || !d_disk || !d_n || n_sweeps < 0) return PMC_E_INVALID;
+    if (n_sweeps == 0) return 0;
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    float4 *cur_d = (float4 *)d_disk, *oth_d = h->scratch_disk;
+    int16_t *cur_n = d_n, *oth_n = h->scratch_n;
+    int pend_on = 0, pend_f = 0;
+    float pend_d = 0.0f;
+    for (int t = 0; t < n_sweeps; t++) {
+        uint64_t sweep = sweep0 + (uint64_t)t;
+        int order[4], f;
+        float d;
+        pmc_schedule(h, sweep, order, &f, &d);
+        SweepArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int k = 0; k < 4; k++) {
+            int off[2];
+            pmc_colour_to_off(order[k], off);
+            a.offx[k] = off[0]; a.offy[k] = off[1];
+        }
+        a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
+        a.shift_on = pend_on; a.shift_f = pend_f; a.shift_d = pend_d;
+        CK(pmc_launch_fused_sweep(h->g, cur_d, cur_n, oth_d, oth_n, a, h->d_ctr, h->stream));
+        rc = exchange_ghosts_async(h, oth_d, oth_n);
+        if (rc) return rc;
+        float4 *td = cur_d; cur_d = oth_d; oth_d = td;
+        int16_t *tn = cur_n; cur_n = oth_n; oth_n = tn;
+        pend_on = 1; pend_f = f; pend_d = d;
+    }
+    CK(pmc_launch_shift(h->g, cur_d, cur_n, oth_d, oth_n, pend_f, pend_d, h->d_ctr, h->stream));
+    rc = exchange_ghosts_async(h, oth_d, oth_n);
+    if (rc) return rc;
+    if (oth_d != (float4 *)d_disk) {
+        CK(cudaMemcpyAsync(d_disk, oth_d, pmc_disk_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(d_n, oth_n, pmc_n_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return finish(h);
+}
+
+// ------------------------------------------------------------------ counters / observables
+int pmc_get_counters(pmc_handle *h, uint64_t *trials, uint64_t *accepted, uint64_t *lost, uint32_t *status)
+{
+    if (!h) return PMC_E_INVALID;
+    Counters c;
+    CK(cudaMemcpyAsync(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (trials) *trials = c.trials;
+    if (accepted) *accepted = c.accepted;
+    if (lost) *lost = c.lost;
+    if (status) *status = c.status;
+    return 0;
+}
+
+int pmc_reset_counters(pmc_handle *h)
+{
+    if (!h) return PMC_E_INVALID;
+    CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
+    return finish(h);
+}
+
+int pmc_check(pmc_handle *h, const float *d_disk, const int16_t *d_n, int64_t out[4], float *min_d2)
+{
+    if (!h || !d_disk || !d_n || !out || !min_d2) return PMC_E_INVALID;
+    CK(pmc_launch_check(h->g, (const float4 *)d_disk, d_n, h->d_out4, h->d_min, h->stream));
+    long long o[4];
+    unsigned bits;
+    CK(cudaMemcpyAsync(o, h->d_out4, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&bits, h->d_min, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4; i++) out[i] = o[i];
+    float m;
+    memcpy(&m, &bits, 4);
+    *min_d2 = (bits == 0x7f7f7f7fu) ? 3.402823466e+38f : m;
+    return 0;
+}
+
+int pmc_gr_hist(pmc_handle *h, const float *d_disk, const int16_t *d_n, float r_max, int nbins, uint64_t *hist_host)
+{
+    if (!h || !d_disk || !d_n || !hist_host || nbins < 1 || nbins > 4096) return PMC_E_INVALID;
+    if (!(r_max > 0.0f) || r_max > h->g.w) return PMC_E_INVALID;
+    if (h->hist_cap < nbins) {
+        cudaFree(h->d_hist); h->d_hist = nullptr; h->hist_cap = 0;
+        CK(cudaMalloc(&h->d_hist, (size_t)nbins * sizeof(unsigned long long)));
+        h->hist_cap = nbins;
+    }
+    CK(pmc_launch_gr_hist(h->g, (const float4 *)d_disk, d_n, r_max, nbins, h->d_hist, h->stream));
+    CK(cudaMemcpyAsync(hist_host, h->d_hist, (size_t)nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// g(r) = pairs / (n_samples * N/2 * rho * shell area); g(sigma+) by a quadratic least-squares
+// fit of the first bins at r >= sigma_d; beta P / rho = 1 + 2 phi g(sigma+)  (2-D virial).
+int pmc_pressure_from_hist(const pmc_handle *h, const uint64_t *hist, float r_max, int nbins,
+                           int64_t n_samples, double *g_of_r, double *g_contact, double *beta_p_over_rho)
+{
+    if (!h || !hist || nbins < 8 || n_samples < 1) return PMC_E_INVALID;
+    const double N = (double)h->p.n_particles, Lb = h->g.L_box;
+    const double rho = N / (Lb * Lb), dr = (double)r_max / nbins, sig = h->p.sigma_d;
+    std::vector<double> gr(nbins);
+    for (int b = 0; b < nbins; b++) {
+        double r0 = b * dr, r1 = r0 + dr;
+        double ideal = (double)n_samples * 0.5 * N * rho * M_PI * (r1 * r1 - r0 * r0);
+        gr[b] = (double)hist[b] / ideal;
+        if (g_of_r) g_of_r[b] = gr[b];
+    }
+    // first bin that lies entirely at r >= sigma
+    int b0 = (int)ceil(sig / dr - 1e-9);
+    int nfit = (int)ceil(0.08 * sig / dr);
+    if (nfit < 4) nfit = 4;
+    if (b0 + nfit > nbins) return PMC_E_INVALID;
+    // least squares g = c0 + c1 t + c2 t^2, t = r_mid - sigma
+    double S[5] = { 0, 0, 0, 0, 0 }, Tv[3] = { 0, 0, 0 };
+    for (int k = 0; k < nfit; k++) {
+        double t = (b0 + k + 0.5) * dr - sig, y = gr[b0 + k], tp = 1.0;
+        for (int m = 0; m < 5; m++) { S[m] += tp; if (m < 3) Tv[m] += tp * y; tp *= t; }
+    }
+    double A[3][4] = { { S[0], S[1], S[2], Tv[0] }, { S[1], S[2], S[3], Tv[1] }, { S[2], S[3], S[4], Tv[2] } };
+    for (int c = 0; c < 3; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 3; r++) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        for (int k = 0; k < 4; k++) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+        if (fabs(A[c][c]) < 1e-300) return PMC_E_INVALID;
+        for (int r = 0; r < 3; r++) if (r != c) {
+            double fct = A[r][c] / A[c][c];
+            for (int k = c; k < 4; k++) A[r][k] -= fct * A[c][k];
+        }
+    }
+    double gc = A[0][3] / A[0][0];
+    double phi_eff = M_PI * sig * sig * rho / 4.0;
+    if (g_contact) *g_contact = gc;
+    if (beta_p_over_rho) *beta_p_over_rho = 1.0 + 2.0 * phi_eff * gc;
+    return 0;
+}
+
+// ------------------------------------------------------------------ host I/O
+int pmc_disk_to_r_host(pmc_handle *h, const float *d_disk, const int16_t *d_n, float *r_host, int64_t *n_found)
+{
+    if (!h || !d_disk || !d_n || !r_host) return PMC_E_INVALID;
+    const DevGeom &g = h->g;
+    size_t db = pmc_disk_bytes(h), nb = pmc_n_bytes(h);
+    std::vector<float> disk(db / sizeof(float));
+    std::vector<int16_t> n(nb / sizeof(int16_t));
+    CK(cudaMemcpyAsync(disk.data(), d_disk, db, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(n.data(), d_n, nb, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // disk_to_r kernel.cu:497-507: cells in order, slots in order (owned rows only)
+    const long long N = h->p.n_particles;
+    long long k = 0;
+    for (int lr = g.ghost; lr < g.ghost + g.rows; lr++) {
+        int cy = g.row0 + (lr - g.ghost);
+        for (int cx = 0; cx < g.cps; cx++) {
+            long long c = (long long)lr * g.cps + cx;
+            double ox = (double)cx * (double)g.w - g.L_box * 0.5, oy = (double)cy * (double)g.w - g.L_box * 0.5;
+            for (int s = 0; s < n[c]; s++) {
+                if (k < N) {
+                    r_host[k] = (float)(ox + (double)disk[c * 16 + s]);
+                    r_host[k + N] = (float)(oy + (double)disk[c * 16 + 8 + s]);
+                }
+                k++;
+            }
+        }
+    }
+    if (n_found) *n_found = k;
+    return 0;
+}
+
+int pmc_run_host(pmc_handle *h, const float *r_host, uint64_t sweep0, int n_sweeps, float *disk_host, int16_t *n_host)
+{
+    if (!h || !r_host || !disk_host || !n_host) return PMC_E_INVALID;
+    if (!h->run_r) CK(cudaMalloc(&h->run_r, pmc_r_bytes(h)));
+    if (!h->run_disk) CK(cudaMalloc(&h->run_disk, pmc_disk_bytes(h)));
+    if (!h->run_n) CK(cudaMalloc(&h->run_n, pmc_n_bytes(h)));
+    const int was_blocking = h->blocking;
+    h->blocking = 0;
+    CK(cudaMemcpyAsync(h->run_r, r_host, pmc_r_bytes(h), cudaMemcpyHostToDevice, h->stream));
+    int rc = pmc_assign(h, h->run_r, (float *)h->run_disk, h->run_n);
+    if (!rc) rc = pmc_sweep(h, (float *)h->run_disk, h->run_n, sweep0, n_sweeps);
+    h->blocking = was_blocking;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(disk_host, h->run_disk, pmc_disk_bytes(h), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(n_host, h->run_n, pmc_n_bytes(h), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ slab ring (NCCL)
+int pmc_comm_unique_id(void *id128)
+{
+    if (!id128) return PMC_E_INVALID;
+    if (!nccl_load()) return PMC_E_COMM;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id)) return PMC_E_COMM;
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int pmc_comm_init(pmc_handle *h, const void *id128)
+{
+    if (!h || !id128) return PMC_E_INVALID;
+    if (h->p.n_ranks <= 1) return 0;
+    if (!nccl_load()) return PMC_E_COMM;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    CK(cudaSetDevice(h->device));
+    if (g_nccl.CommInitRank(&h->comm, h->p.n_ranks, id, h->p.rank)) return PMC_E_COMM;
+    return 0;
+}
+
+int pmc_exchange_ghosts(pmc_handle *h, float *d_disk, int16_t *d_n)
+{
+    if (!h || !d_disk || !d_n) return PMC_E_INVALID;
+    int rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
+    if (rc) return rc;
+    return finish(h);
+}
+
+}  // extern "C"

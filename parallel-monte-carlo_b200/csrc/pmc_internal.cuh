@@ -1,0 +1,141 @@
+// pmc_internal.cuh -- shared between the translation units of libpmc_b200.so.
+// B200 (sm_100a) only.  Every float operation that takes part in a parity contract is an
+// explicit round-to-nearest intrinsic (__fadd_rn / __fmul_rn / __fmaf_rn / __f*2_rn), so nvcc
+// can neither contract nor reassociate it and results are bit-identical to oracle/pmc_oracle.c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pmc.h"
+
+#define PMC_NMAX 8          // slots per cell in this build: one cell = 4 x float4 = 64 B
+
+// geometry + slab description, passed by value to every kernel
+struct DevGeom {
+    int cps;                // cellsPerSide (whole box)
+    int row0;               // first owned cell row (global)
+    int rows;               // owned rows
+    int ghost;              // ghost rows on each side (0 when single rank)
+    int local_rows;         // rows + 2*ghost
+    int wrap_y;             // 1: single rank, rows wrap modulo cps
+    int n_M;
+    float w;
+    float sigma;
+    float sigma2;
+    float dscale;           // move_delta * 2^-24
+    float L;
+    float half_L;
+    double L_box;
+    unsigned seed_lo, seed_hi;
+    long long n_particles;
+};
+
+struct Counters {           // device-resident, one per handle
+    unsigned long long trials;
+    unsigned long long accepted;
+    unsigned long long lost;
+    unsigned int status;
+    unsigned int pad;
+};
+
+struct SweepArgs {
+    int offx[4], offy[4];   // colour offsets in execution order (itoa start.cu:153-157)
+    unsigned sweep_lo, sweep_hi;
+    int shift_on;           // apply a pending shiftCells(f, d) while loading
+    int shift_f;
+    float shift_d;
+};
+
+// ---- launchers implemented in the .cu files (all asynchronous on `st`)
+cudaError_t pmc_launch_init_r(const DevGeom &g, float *d_r, cudaStream_t st);
+cudaError_t pmc_launch_assign(const DevGeom &g, const float *d_r, float4 *disk, int16_t *n,
+                              Counters *ctr, cudaStream_t st);
+cudaError_t pmc_launch_shift(const DevGeom &g, const float4 *src, const int16_t *nsrc,
+                             float4 *dst, int16_t *ndst, int f, float d, Counters *ctr,
+                             cudaStream_t st);
+cudaError_t pmc_launch_subsweep(const DevGeom &g, float4 *disk, const int16_t *n,
+                                const SweepArgs &a, Counters *ctr, cudaStream_t st);
+cudaError_t pmc_launch_fused_sweep(const DevGeom &g, const float4 *din, const int16_t *nin,
+                                   float4 *dout, int16_t *nout, const SweepArgs &a,
+                                   Counters *ctr, cudaStream_t st);
+cudaError_t pmc_launch_check(const DevGeom &g, const float4 *disk, const int16_t *n,
+                             long long *out4, unsigned *min_d2_bits, cudaStream_t st);
+cudaError_t pmc_launch_gr_hist(const DevGeom &g, const float4 *disk, const int16_t *n,
+                               float r_max, int nbins, unsigned long long *hist, cudaStream_t st);
+int pmc_fused_launch_count();   // kernels per fused sweep (for bench gpu_launches)
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ Philox4x32-10
+// Salmon et al., SC'11.  Counter = {cell id, sweep lo, sweep hi, call}, key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1,
+                                              uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ int wrap_mod(int v, int m)
+{
+    v %= m;
+    return v < 0 ? v + m : v;
+}
+
+// one cell in registers: x[8], y[8] as four float4 (global layout [cell][dim][slot])
+struct CellRegs {
+    float4 x03, x47, y03, y47;
+    int cnt;
+};
+
+__device__ __forceinline__ float f4get(const float4 &lo, const float4 &hi, int i)
+{
+    // static index after unrolling
+    switch (i) {
+    case 0: return lo.x; case 1: return lo.y; case 2: return lo.z; case 3: return lo.w;
+    case 4: return hi.x; case 5: return hi.y; case 6: return hi.z; default: return hi.w;
+    }
+}
+
+// V2 shiftCells.h:23-112 for one destination cell in cell-local coordinates: stayers of
+// `own` in slot order, then immigrants from `up` (the cell at +dir along axis F) in slot
+// order.  put(slot, f_coord, other_coord) stores one particle; returns the new count
+// (clamped to PMC_NMAX) and the number of particles that did not fit in *dropped.
+template <int F, typename Put>
+__device__ __forceinline__ int shift_one_cell(const CellRegs &own, const CellRegs &up,
+                                              float d, float w, float sshift, Put put, int *dropped)
+{
+    int nNew = 0, drop = 0;
+#pragma unroll
+    for (int i = 0; i < PMC_NMAX; i++) {
+        float fc = F == 0 ? f4get(own.x03, own.x47, i) : f4get(own.y03, own.y47, i);
+        float oc = F == 0 ? f4get(own.y03, own.y47, i) : f4get(own.x03, own.x47, i);
+        float D = __fadd_rn(fc, -d);
+        if (i < own.cnt && D > 0.0f && D <= w) {           // shiftCells.h:62
+            put(nNew, D, oc);                              // nNew < 8 always holds here
+            nNew++;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PMC_NMAX; i++) {
+        float fc = F == 0 ? f4get(up.x03, up.x47, i) : f4get(up.y03, up.y47, i);
+        float oc = F == 0 ? f4get(up.y03, up.y47, i) : f4get(up.x03, up.x47, i);
+        float D = __fadd_rn(fc, -d);
+        if (i < up.cnt && !(D > 0.0f && D <= w)) {         // shiftCells.h:94
+            if (nNew < PMC_NMAX) {
+                put(nNew, __fadd_rn(D, sshift), oc);       // shiftCells.h:97
+                nNew++;
+            } else drop++;
+        }
+    }
+    *dropped = drop;
+    return nNew;
+}
+#endif  // __CUDACC__

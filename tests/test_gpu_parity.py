@@ -1,0 +1,249 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C-ABI against the CPU
+oracle on the same seeded inputs.  Integer / index results and float positions are compared
+BIT-EXACTLY (both sides use the same individually rounded IEEE binary32 operations)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1, seed=1234)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def pair(N, **over):
+    import pmc_b200
+    from oracle import oracle as O
+    kw = dict(KW, **over)
+    return pmc_b200.ParallelMC(N, **kw), O.Oracle(N, **kw)
+
+
+def assert_same_state(disk, n, odisk, on):
+    assert np.array_equal(n.cpu().numpy(), on)
+    d = disk.cpu().numpy()
+    if not np.array_equal(bits(d), bits(odisk)):
+        bad = np.nonzero((bits(d) != bits(odisk)).any(axis=(1, 2)))[0]
+        raise AssertionError(f"{len(bad)} cells differ, first {bad[:8]}: gpu {d[bad[0]]} oracle {odisk[bad[0]]}")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(built):
+    return built
+
+
+# ---------------------------------------------------------------- init_r / assign
+@pytest.mark.parametrize("N", [16, 4096, 2 ** 20])
+def test_init_r_bit_exact(N):
+    mc, o = pair(N)
+    assert np.array_equal(bits(mc.init_r().cpu().numpy()), bits(o.init_r()))
+    g = mc.geom
+    assert (g.cps, g.w, g.L) == (o.g.cps, o.g.w, o.g.L)
+
+
+@pytest.mark.parametrize("N,phi", [(4096, 0.70), (2 ** 16, 0.70), (2 ** 20, 0.70), (2 ** 18, 0.30)])
+def test_assign_lattice_bit_exact(N, phi):
+    mc, o = pair(N, phi=phi)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    assert_same_state(disk, n, odisk, on)
+    assert mc.counters()["status"] == 0
+
+
+def test_assign_random_points_slot_order_and_lost():
+    import torch
+    mc, o = pair(2 ** 14, phi=0.2)
+    rng = np.random.default_rng(3)
+    r = ((rng.random((2, 2 ** 14)) - 0.5) * o.g.L * 1.002).astype(np.float32)   # a few outside the box
+    odisk, on = o.assign(r)
+    disk, n = mc.assign(torch.from_numpy(r).cuda())
+    c = mc.counters()
+    assert o.lost > 0 and c["lost"] == o.lost and (c["status"] & 2)
+    if not (c["status"] & 1):            # no overflow: slot order must be the reference's
+        assert_same_state(disk, n, odisk, on)
+
+
+def test_empty_and_ragged_cells():
+    """N=16 particles in a 4x4-cell box after shifting: empty cells, ragged counts."""
+    import torch
+    mc, o = pair(64, phi=0.05)
+    r = o.init_r()
+    r[:, 40:] = r[:, :24] * 0.31 + 0.07          # pile particles up: ragged, some cells empty
+    odisk, on = o.assign(r)
+    disk, n = mc.assign(torch.from_numpy(r).cuda())
+    assert_same_state(disk, n, odisk, on)
+    assert (on == 0).any()
+    mc.sweep(disk, n, 0, 7)
+    o.sweep(odisk, on, 0, 7)
+    assert_same_state(disk, n, odisk, on)
+
+
+# ---------------------------------------------------------------- sub-sweep, one colour at a time
+@pytest.mark.parametrize("N", [4096, 2 ** 16])
+def test_subsweep_each_colour_bit_exact(N):
+    mc, o = pair(N)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    for sweep in range(3):
+        for colour in (2, 0, 3, 1):
+            off = o.colour_to_off(colour)
+            mc.subsweep(disk, n, off, sweep)
+            o.subsweep(odisk, on, off, sweep)
+            assert_same_state(disk, n, odisk, on)
+    c = mc.counters()
+    assert (c["trials"], c["accepted"]) == (o.trials.value, o.accepted.value)
+
+
+@pytest.mark.parametrize("f,dfrac", [(0, 0.25), (0, -0.31), (1, 0.5), (1, -0.4999), (0, 0.0)])
+def test_shift_cells_bit_exact(f, dfrac):
+    mc, o = pair(2 ** 14)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    o.sweep(odisk, on, 0, 2)
+    mc.sweep(disk, n, 0, 2)
+    d = np.float32(dfrac * o.g.w)
+    mc.shift_cells(disk, n, f, float(d))
+    o.shift_cells(odisk, on, f, d)
+    assert_same_state(disk, n, odisk, on)
+
+
+def test_schedule_matches_oracle():
+    mc, o = pair(4096)
+    for s in list(range(50)) + [2 ** 32 + 5, 2 ** 40]:
+        order, f, d = mc.schedule(s)
+        oorder, of, od = o.schedule(s)
+        assert order == oorder and f == of and np.float32(d) == od
+
+
+# ---------------------------------------------------------------- the fused sweep = protocol of start.cu:237-260
+@pytest.mark.parametrize("N,sweeps,over", [
+    (4096, 25, {}),                                  # BASELINE config 1 geometry (cps = 32, one tile)
+    (2 ** 14, 6, {}),                                # 2 x 2 tiles
+    (2 ** 16, 4, {}),                                # 5 x 5 tiles, partial edge tiles
+    (2 ** 16, 3, dict(n_M=7)),                       # odd n_M, more trials than particles
+    (2 ** 16, 3, dict(n_M=1)),
+    (2 ** 14, 4, dict(phi=0.30, move_delta=0.4)),    # dilute (config 5 regime): empty cells
+    (2 ** 14, 4, dict(cell_w=1.5, phi=0.5)),         # w < 2 sigma: generic 3x3 path
+    (2 ** 14, 4, dict(cell_w=2.6, phi=0.6)),         # w > 2 sigma: trials that need no neighbour column
+    (2 ** 14, 3, dict(seed=2 ** 40 + 17)),
+])
+def test_fused_sweep_bit_exact(N, sweeps, over):
+    mc, o = pair(N, **over)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    mc.sweep(disk, n, 0, sweeps)
+    o.sweep(odisk, on, 0, sweeps)
+    assert_same_state(disk, n, odisk, on)
+    c = mc.counters()
+    assert (c["trials"], c["accepted"], c["lost"]) == (o.trials.value, o.accepted.value, o.lost)
+    assert c["status"] == 0
+
+
+def test_fused_equals_per_call_protocol_and_split_calls():
+    """pmc_sweep(K) == K x (4 x pmc_subsweep + pmc_shift_cells) == pmc_sweep(a) + pmc_sweep(K-a)."""
+    mc, o = pair(2 ** 14)
+    r = mc.init_r()
+    d1, n1 = mc.assign(r)
+    d2, n2 = mc.assign(r)
+    d3, n3 = mc.assign(r)
+    mc.sweep(d1, n1, 0, 5)
+    for s in range(5):
+        order, f, d = mc.schedule(s)
+        for c in order:
+            mc.subsweep(d2, n2, mc.colour_to_off(c), s)
+        mc.shift_cells(d2, n2, f, d)
+    mc.sweep(d3, n3, 0, 2)
+    mc.sweep(d3, n3, 2, 3)
+    assert_same_state(d2, n2, d1.cpu().numpy(), n1.cpu().numpy())
+    assert_same_state(d3, n3, d1.cpu().numpy(), n1.cpu().numpy())
+
+
+def test_garbage_in_unused_slots_is_tolerated():
+    """The reference leaves garbage in slots >= n[cell] (shiftCells.h:108-110 copies it around);
+    the C-ABI must not let it influence results."""
+    import torch
+    mc, o = pair(2 ** 14)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    mask = (torch.arange(8, device="cuda")[None, :] >= n[:, None].to(torch.int64))
+    junk = torch.rand_like(disk) * 2.0
+    disk[:, 0, :] = torch.where(mask, junk[:, 0, :], disk[:, 0, :])
+    disk[:, 1, :] = torch.where(mask, junk[:, 1, :], disk[:, 1, :])
+    mc.sweep(disk, n, 0, 3)
+    o.sweep(odisk, on, 0, 3)
+    assert_same_state(disk, n, odisk, on)
+
+
+# ---------------------------------------------------------------- observables
+def test_check_and_gr_hist_bit_exact():
+    mc, o = pair(2 ** 16)
+    disk, n = mc.assign(mc.init_r())
+    mc.sweep(disk, n, 0, 10)
+    d, nn = disk.cpu().numpy(), n.cpu().numpy()
+    g, oc = mc.check(disk, n), o.check(d, nn)
+    assert (g["total"], g["out_of_cell"], g["overlaps"], g["bad_sentinels"]) == \
+           (oc["total"], oc["out_of_cell"], oc["overlaps"], oc["bad_sentinels"])
+    assert np.float32(g["min_d2"]) == oc["min_d2"]
+    assert g["total"] == 2 ** 16 and g["out_of_cell"] == 0
+    assert g["min_d2"] > 1.0 - 1e-5
+    h = mc.gr_hist(disk, n, 2.0, 512)
+    assert np.array_equal(h, o.gr_hist(d, nn, 2.0, 512))
+    gr, gc, bp = mc.pressure_from_hist(h, 2.0, 1)
+    assert gr[: 250].max() == 0.0 and 2.0 < gc < 12.0 and bp > 1.0
+
+
+def test_overflow_is_reported_not_silent():
+    """8 < particles in one cell: the reference writes out of bounds (start.cu:135-138);
+    we must flag it."""
+    import torch
+    mc, o = pair(4096, sigma_d=0.01, phi=0.70 * 1e-4)
+    r = o.init_r()
+    r[:, :12] = r[:, :1] + (np.arange(12, dtype=np.float32) * 1e-3)[None, :]
+    disk, n = mc.assign(torch.from_numpy(r).cuda())
+    c = mc.counters()
+    assert c["status"] & 1 and c["lost"] >= 1
+    assert int(n.max()) <= 8
+
+
+# ---------------------------------------------------------------- end to end with host buffers
+def test_run_host_round_trip():
+    import torch
+    mc, o = pair(2 ** 14)
+    r = o.init_r()
+    rh = torch.from_numpy(r).pin_memory()
+    g = mc.geom
+    dh = torch.empty((g.local_cells, 2, 8), dtype=torch.float32).pin_memory()
+    nh = torch.empty((g.local_cells,), dtype=torch.int16).pin_memory()
+    mc.run_host(rh, 0, 4, dh, nh)
+    odisk, on = o.assign(r)
+    o.sweep(odisk, on, 0, 4)
+    assert np.array_equal(nh.numpy(), on) and np.array_equal(bits(dh.numpy()), bits(odisk))
+    # global coordinates back on the host (disk_to_r kernel.cu:497-507)
+    disk, n = torch.from_numpy(odisk).cuda(), torch.from_numpy(on).cuda()
+    rg, k = mc.disk_to_r_host(disk, n)
+    ro, ko = o.disk_to_r(odisk, on)
+    assert k == ko == 2 ** 14 and np.array_equal(bits(rg), bits(ro))
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE sizes)
+@pytest.mark.parametrize("N,phi,sweeps", [(2 ** 20, 0.70, 20), (2 ** 24, 0.70, 10), (2 ** 22, 0.30, 10)])
+def test_full_size_invariants(N, phi, sweeps):
+    import pmc_b200
+    mc = pmc_b200.ParallelMC(N, **dict(KW, phi=phi, move_delta=0.1 if phi > 0.5 else 0.4))
+    disk, n = mc.assign(mc.init_r())
+    mc.sweep(disk, n, 0, sweeps)
+    g = mc.check(disk, n)
+    c = mc.counters()
+    assert g["total"] == N and g["out_of_cell"] == 0 and g["bad_sentinels"] == 0
+    assert g["min_d2"] > 1.0 - 1e-5 and c["status"] == 0 and c["lost"] == 0
+    nonempty_bound = mc.geom.n_cells * 4 * sweeps
+    assert 0 < c["trials"] <= nonempty_bound
+    if phi > 0.5:
+        assert c["trials"] == nonempty_bound          # no empty cells at phi = 0.70
+    assert 0.05 < c["accepted"] / c["trials"] < 0.95
+    # determinism: same inputs, same bits
+    d2, n2 = mc.assign(mc.init_r())
+    mc.sweep(d2, n2, 0, sweeps)
+    import torch
+    assert torch.equal(disk.view(torch.int32), d2.view(torch.int32)) and torch.equal(n, n2)

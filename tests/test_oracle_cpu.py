@@ -1,0 +1,271 @@
+"""CPU tests: pin the oracle (oracle/pmc_oracle.c) against known answers, the reference's own
+golden data and the reference's literal rules restated independently in numpy."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KW = dict(phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1, seed=1234)
+
+
+# ---------------------------------------------------------------- Philox4x32-10 known answers
+# Random123 v1.09 kat_vectors (philox4x32 10): counter, key -> output
+KAT = [
+    ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+]
+
+
+@pytest.mark.parametrize("ctr,key,expect", KAT)
+def test_philox_kat(ctr, key, expect):
+    assert O.philox(ctr, key) == expect
+
+
+# ---------------------------------------------------------------- geometry
+@pytest.mark.parametrize("N,phi,cps,mult", [
+    (4096, 0.70, 32, 2), (2 ** 20, 0.70, 542, 2), (2 ** 24, 0.716, 2144, 2),
+    (2 ** 24, 0.70, 2168, 2), (2 ** 28, 0.70, 8672, 16), (2 ** 22, 0.30, 1656, 2)])
+def test_geometry_table(N, phi, cps, mult):
+    kw = dict(KW, phi=phi, cps_multiple=mult)
+    o = O.Oracle(N, **kw)
+    assert o.cps == cps
+    assert o.g.w >= 2.0 and o.g.w < 2.2
+    assert abs(o.g.L - np.sqrt(N * np.pi / (4 * phi))) < 1e-3 * o.g.L
+
+
+# ---------------------------------------------------------------- init_r vs the reference's own dump
+def test_init_r_matches_reference_dump_frame0():
+    gold = json.load(open(os.path.join(HERE, "golden", "dumpR3_frame0.json")))
+    xyz = np.array(gold["xyz"])
+    g = O.Geom()
+    g.n_particles = 16
+    g.L = gold["L"]
+    r = np.zeros((2, 16), dtype=np.float32)
+    assert O.lib().oracle_init_r(C.byref(g), r.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    # the reference's first z-layer (atoms 0..15) is the 2-D lattice: ix fastest, then iy
+    np.testing.assert_allclose(r[0], xyz[:16, 0], atol=5e-7)
+    np.testing.assert_allclose(r[1], xyz[:16, 1], atol=5e-7)
+
+
+def test_init_r_requires_square():
+    o = O.Oracle(4096, **KW)
+    o.g.n_particles = 4095
+    with pytest.raises(ValueError):
+        o.init_r()
+
+
+# ---------------------------------------------------------------- assign vs the literal reference rule
+def ref_assign_numpy(o, r):
+    """start.cu:125-141 literally: every cell scans all atoms, lb < x <= ub, float32."""
+    g = o.g
+    w, hl = np.float32(g.w), np.float32(g.half_L)
+    c = np.arange(g.cps, dtype=np.float32)
+    lb = (c * w).astype(np.float32) - hl                  # xlb = cellx*w - L/2.0f
+    ub = (lb + w).astype(np.float32)                      # xub = xlb + w
+    members = {}
+    x, y = r[0], r[1]
+    inx = (x[None, :] <= ub[:, None]) & (x[None, :] > lb[:, None])     # [cell, atom]
+    iny = (y[None, :] <= ub[:, None]) & (y[None, :] > lb[:, None])
+    for cy in range(g.cps):
+        for cx in range(g.cps):
+            idx = np.nonzero(inx[cx] & iny[cy])[0]
+            if len(idx):
+                members[cx + cy * g.cps] = idx
+    return members, inx.sum(0), iny.sum(0)
+
+
+@pytest.mark.parametrize("N,seed", [(1024, 1), (4096, 2)])
+def test_assign_matches_reference_rule(N, seed):
+    o = O.Oracle(N, **dict(KW, phi=0.25))       # random points: keep Poisson tails below nmax
+    rng = np.random.default_rng(seed)
+    L = o.g.L
+    r = ((rng.random((2, N)) - 0.5) * L * 0.999).astype(np.float32)
+    disk, n = o.assign(r)
+    members, nx, ny = ref_assign_numpy(o, r)
+    # wherever the literal rule conserves particles (exactly one cell per axis) it must agree
+    ok = (nx == 1) & (ny == 1)
+    assert ok.mean() > 0.99
+    r2, k = o.disk_to_r(disk, n)
+    for cell, idx in members.items():
+        idx = idx[ok[idx]]
+        if n[cell] > len(idx):      # a particle the literal rule dropped/duplicated landed here
+            continue
+        cnt = n[cell]
+        assert cnt == min(len(idx), 8), (cell, cnt, idx)
+        idx = idx[:cnt]                 # overflow: the oracle keeps the first nmax in atom order
+        # slot order = ascending atom index; positions round-trip through cell-local coords
+        cx, cy = cell % o.cps, cell // o.cps
+        gx = np.float32(cx * np.float64(o.g.w) - o.g.L_box / 2) + disk[cell, 0, :cnt]
+        np.testing.assert_allclose(gx, r[0, idx], atol=2e-5)
+        gy = np.float32(cy * np.float64(o.g.w) - o.g.L_box / 2) + disk[cell, 1, :cnt]
+        np.testing.assert_allclose(gy, r[1, idx], atol=2e-5)
+    assert n.sum() + o.lost == N
+    chk = o.check(disk, n)
+    assert chk["out_of_cell"] == 0 and chk["bad_sentinels"] == 0
+
+
+def test_assign_lattice_config1():
+    o = O.Oracle(4096, **KW)
+    disk, n = o.assign(o.init_r())
+    assert o.lost == 0 and (n == 4).all()
+    chk = o.check(disk, n)
+    assert chk["total"] == 4096 and chk["overlaps"] == 0 and chk["out_of_cell"] == 0
+
+
+def test_assign_out_of_box_is_lost():
+    o = O.Oracle(1024, **KW)
+    r = o.init_r()
+    r[0, 5] = o.g.L        # outside the box: the reference drops it silently
+    disk, n = o.assign(r)
+    assert o.lost == 1 and n.sum() == 1023
+
+
+# ---------------------------------------------------------------- shiftCells semantics
+def global_positions(o, disk, n):
+    out = []
+    for cell in range(o.n_cells):
+        cx, cy = cell % o.cps, cell // o.cps
+        for s in range(n[cell]):
+            out.append((cx * float(o.g.w) + float(disk[cell, 0, s]), cy * float(o.g.w) + float(disk[cell, 1, s])))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("f,dfrac", [(0, 0.25), (0, -0.25), (1, 0.5), (1, -0.4999), (0, 0.0), (1, 1e-4)])
+def test_shift_cells_semantics(f, dfrac):
+    """Net effect of shiftCells (shiftCells.h:23-112): every particle's f coordinate becomes
+    x - d (mod L); membership stays (0, w]; stayers keep slot order, immigrants follow."""
+    o = O.Oracle(1024, **KW)
+    disk, n = o.assign(o.init_r())
+    o.sweep(disk, n, 0, 3)                       # decorrelate from the lattice
+    before = global_positions(o, disk, n)
+    d0, n0 = disk.copy(), n.copy()
+    d = np.float32(dfrac * o.g.w)
+    o.shift_cells(disk, n, f, d)
+    after = global_positions(o, disk, n)
+    assert n.sum() == 1024 and o.lost == 0
+    Lb = o.cps * float(o.g.w)
+    exp = before.copy()
+    exp[:, f] = (exp[:, f] - float(d)) % Lb
+    # compare as multisets of points on the torus
+    def key(a):
+        return np.lexsort((np.round(a[:, 1], 3), np.round(a[:, 0], 3)))
+    a, e = after[key(after)], exp[key(exp)]
+    diff = np.abs(a - e)
+    diff = np.minimum(diff, Lb - diff)
+    assert diff.max() < 1e-4
+    chk = o.check(disk, n)
+    assert chk["out_of_cell"] == 0 and chk["bad_sentinels"] == 0
+    # slot order: stayers first in old order, then immigrants in the neighbour's slot order
+    w = o.g.w
+    dirn = -1 if d <= 0 else 1
+    for cell in range(o.n_cells):
+        cx, cy = cell % o.cps, cell // o.cps
+        stay = [np.float32(d0[cell, f, s] - d) for s in range(n0[cell])]
+        stay = [D for D in stay if D > 0 and D <= w]
+        nb = ((cx + dirn) % o.cps + cy * o.cps) if f == 0 else (cx + ((cy + dirn) % o.cps) * o.cps)
+        imm = [np.float32(d0[nb, f, s] - d) for s in range(n0[nb])]
+        imm = [np.float32(D + np.float32(w * dirn)) for D in imm if not (D > 0 and D <= w)]
+        got = list(disk[cell, f, :n[cell]])
+        assert got == stay + imm
+
+
+# ---------------------------------------------------------------- sub-sweep structure
+def test_subsweep_touches_only_active_colour():
+    o = O.Oracle(4096, **KW)
+    disk, n = o.assign(o.init_r())
+    before = disk.copy()
+    o.subsweep(disk, n, [1, 0], 0)
+    changed = np.nonzero((disk != before).any(axis=(1, 2)))[0]
+    assert len(changed) > 100
+    assert ((changed % o.cps) % 2 == 1).all() and ((changed // o.cps) % 2 == 0).all()
+    assert o.trials.value == 4 * (o.n_cells // 4)        # n_M trials per non-empty active cell
+    assert 0 < o.accepted.value < o.trials.value
+
+
+def test_subsweep_same_sweep_same_stream_different_sweep_differs():
+    o1, o2, o3 = (O.Oracle(4096, **KW) for _ in range(3))
+    r = o1.init_r()
+    (d1, n1), (d2, n2), (d3, n3) = o1.assign(r), o2.assign(r), o3.assign(r)
+    o1.subsweep(d1, n1, [0, 0], 7)
+    o2.subsweep(d2, n2, [0, 0], 7)
+    o3.subsweep(d3, n3, [0, 0], 8)
+    assert np.array_equal(d1, d2) and not np.array_equal(d1, d3)
+
+
+def test_schedule_is_uniform_and_in_range():
+    o = O.Oracle(4096, **KW)
+    firsts = np.zeros(4)
+    fs = []
+    ds = []
+    for s in range(4000):
+        order, f, d = o.schedule(s)
+        assert sorted(order) == [0, 1, 2, 3]
+        firsts[order[0]] += 1
+        fs.append(f)
+        ds.append(d)
+    ds = np.array(ds)
+    assert (ds > -o.g.w / 2).all() and (ds <= o.g.w / 2).all()
+    assert abs(np.mean(fs) - 0.5) < 0.05 and (np.abs(firsts / 4000 - 0.25) < 0.04).all()
+    assert abs(ds.mean()) < 0.06 * o.g.w
+    assert O.Oracle.colour_to_off(0) == [0, 0] and O.Oracle.colour_to_off(1) == [0, 1]
+    assert O.Oracle.colour_to_off(2) == [1, 0] and O.Oracle.colour_to_off(3) == [1, 1]
+
+
+# ---------------------------------------------------------------- full protocol invariants (config 1, shortened)
+def test_config1_invariants_and_omp_identity():
+    o = O.Oracle(4096, **KW)
+    disk, n = o.assign(o.init_r())
+    o.sweep(disk, n, 0, 60)
+    chk = o.check(disk, n)
+    assert chk["total"] == 4096 and chk["out_of_cell"] == 0 and chk["bad_sentinels"] == 0
+    assert chk["overlaps"] == 0 or chk["min_d2"] > 1.0 - 1e-5
+    assert o.lost == 0
+    acc = o.accepted.value / o.trials.value
+    assert 0.2 < acc < 0.6
+    # OpenMP variant (timed CPU baseline) is bit-identical to the serial one
+    p = O.Oracle(4096, **KW)
+    pd, pn = p.assign(p.init_r())
+    p.sweep(pd, pn, 0, 60, omp=True)
+    assert np.array_equal(pd.view(np.uint32), disk.view(np.uint32)) and np.array_equal(pn, n)
+    assert p.trials.value == o.trials.value and p.accepted.value == o.accepted.value
+
+
+def test_ideal_gas_occupancy_stays_uniform():
+    """Detailed-balance smoke test: with sigma_d -> 0 the stationary distribution is
+    uniform; cell occupancies must stay Poisson-like (variance ~ mean) under sweeps + shifts."""
+    N = 512
+    phi = N * np.pi * 1e-6 / (4 * 64.0 ** 2) * 0.9999
+    kw = dict(KW, sigma_d=1e-3, cell_w=2.0, phi=phi, move_delta=0.7)
+    o = O.Oracle(N, **kw)
+    assert o.cps == 32
+    rng = np.random.default_rng(5)
+    r = ((rng.random((2, N)) - 0.5) * o.g.L * 0.9999).astype(np.float32)
+    disk, n = o.assign(r)
+    assert n.sum() == N and o.lost == 0
+    var_ratio = []
+    for k in range(20):
+        o.sweep(disk, n, 10 * k, 10)
+        var_ratio.append(n.var() / n.mean())
+    assert n.sum() == N and o.lost == 0
+    assert abs(np.mean(var_ratio) - 1.0) < 0.1          # Poisson: variance == mean
+    assert o.accepted.value / o.trials.value > 0.5
+
+
+def test_gr_hist_counts_pairs_once():
+    o = O.Oracle(1024, **KW)
+    disk, n = o.assign(o.init_r())
+    h = o.gr_hist(disk, n, 2.0, 200)
+    # square lattice spacing a = L/32: 4 nearest neighbours per particle -> 2 pairs per particle
+    a = o.g.L / 32
+    b = int(a * 200 / 2.0)
+    assert h[b - 1:b + 2].sum() == 2 * 1024
+    b2 = int(a * np.sqrt(2) * 200 / 2.0)
+    assert h[b2 - 1:b2 + 2].sum() == 2 * 1024
+    assert h[:b - 1].sum() == 0
