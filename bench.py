@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- hard-disk trial moves/sec (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # ours, N=2^24 phi=0.70 on one B200
+    torchrun ... bench.py --gpus N --steps K --warmup W      # ours, N=2^28 slabs over N B200s
+    python bench.py --impl reference ...                     # the CPU path (oracle, all host cores)
+
+A "step" is one pass of the hot path over one batch: `sweeps_per_step` full MC sweeps
+(each = 4 checkerboard sub-sweeps + grid shift, start.cu:237-260) of the resident system.
+value  = trial moves actually executed (device-counted) / device time, inputs resident in HBM.
+e2e    = the same through pmc_run_host with HOST buffers: H2D(r) + assign + sweeps + D2H(disk, n).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, phi, cps_multiple, move_delta)
+    "n16m_phi0.70": (2 ** 24, 0.70, 2, 0.1),       # BASELINE metric config (1 GPU)
+    "n256m_phi0.70": (2 ** 28, 0.70, 16, 0.1),     # BASELINE config 4 (1/2/4/8 GPUs)
+    "n1m_phi0.70": (2 ** 20, 0.70, 2, 0.1),        # config 2
+    "n16m_phi0.716": (2 ** 24, 0.716, 2, 0.1),     # config 3
+    "n4m_phi0.30": (2 ** 22, 0.30, 2, 0.4),        # config 5 (dilute)
+    "n4096_phi0.70": (4096, 0.70, 2, 0.1),         # config 1
+}
+N_M, NMAX, SIGMA, CELL_W, SEED = 4, 8, 1.0, 2.0, 1234
+METRIC = "hard-disk trial moves/sec"
+UNIT = "moves/s"
+
+# ncu --set full capture of sweep_tile_kernel<4,...> at N=2^24 (profiles/): dram bytes per launch
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def algorithmic_bytes_per_sweep(n_particles, n_cells):
+    """56 B per particle per sweep + 12 B per cell per sweep."""
+    return 56.0 * n_particles + 12.0 * n_cells
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(workload, sweeps, omp=True):
+    """The reference has no CPU path; the CPU baseline is our C restatement
+    (oracle/, kind="port"), OpenMP over same-colour cells on all host cores."""
+    from oracle import oracle as O
+    N, phi, mult, delta = WORKLOADS[workload]
+    o = O.Oracle(N, phi=phi, sigma_d=SIGMA, cell_w=CELL_W, nmax=NMAX, n_M=N_M, move_delta=delta,
+                 seed=SEED, cps_multiple=mult)
+    disk, n = o.assign(o.init_r())
+    t0 = time.perf_counter()
+    threads = o.sweep(disk, n, 0, sweeps, omp=omp)
+    dt = time.perf_counter() - t0
+    return o.trials.value / dt, threads, dt, o
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path on the box's host cores, rank 0 only."""
+    if rank != 0:
+        return
+    workload = args.workload or ("n16m_phi0.70" if args.gpus == 1 else "n256m_phi0.70")
+    sample_wl = workload if WORKLOADS[workload][0] <= 2 ** 24 else "n16m_phi0.70"
+    sweeps = args.ref_sweeps
+    from oracle import oracle as O
+    N, phi, mult, delta = WORKLOADS[sample_wl]
+    o = O.Oracle(N, phi=phi, sigma_d=SIGMA, cell_w=CELL_W, nmax=NMAX, n_M=N_M, move_delta=delta,
+                 seed=SEED, cps_multiple=mult)
+    disk, n = o.assign(o.init_r())
+    threads = 1
+    for w in range(min(args.warmup, 1)):
+        threads = o.sweep(disk, n, 0, 1, omp=True)
+    tr0 = o.trials.value
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        threads = o.sweep(disk, n, 1 + k * sweeps, sweeps, omp=True)
+    dt = time.perf_counter() - t0
+    v = (o.trials.value - tr0) / dt
+    sample = f"{sample_wl}: {sweeps} sweeps/step from the lattice start, OpenMP over same-colour cells"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "sample_workload": sample_wl, "n_M": N_M, "nmax": NMAX,
+                   "cell_w": o.g.w, "move_delta": delta, "sweeps_per_step": sweeps,
+                   "proposal": "uniform square"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--sweeps-per-step", type=int, default=100)
+    ap.add_argument("--burn-in", type=int, default=300)
+    ap.add_argument("--ref-sweeps", type=int, default=2, help="sweeps per step of the CPU arm")
+    ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import pmc_b200
+    import __graft_entry__ as ge
+    if rank == 0 and pmc_b200._stale():
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    n_ranks = world
+
+    workload = args.workload or ("n16m_phi0.70" if n_ranks == 1 else "n256m_phi0.70")
+    N, phi, mult, delta = WORKLOADS[workload]
+    if n_ranks > 1:
+        mult = max(mult, 2 * n_ranks)
+    W = max(args.warmup, 3)
+    S = args.sweeps_per_step
+
+    mc = pmc_b200.ParallelMC(N, phi=phi, sigma_d=SIGMA, cell_w=CELL_W, nmax=NMAX, n_M=N_M,
+                             move_delta=delta, seed=SEED, cps_multiple=mult, device=local_rank,
+                             rank=rank, n_ranks=n_ranks)
+    if n_ranks > 1:
+        mc.comm_init_from_torch()
+    g = mc.geom
+    r = mc.init_r()
+    disk, n = mc.assign(r)
+    del r
+    torch.cuda.empty_cache()
+    mc.set_blocking(0)
+    sweep = 0
+    mc.sweep(disk, n, sweep, args.burn_in)          # melt the lattice
+    sweep += args.burn_in
+    for _ in range(W):
+        mc.sweep(disk, n, sweep, S)
+        sweep += S
+    torch.cuda.synchronize()
+    mc.reset_counters()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mc.sweep(disk, n, sweep, S)
+        sweep += S
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    c = mc.counters()
+    trials = torch.tensor([c["trials"], c["accepted"], c["lost"], c["status"]], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(trials, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    tot_trials, tot_acc, tot_lost, status = (float(x) for x in trials.tolist())
+    value = tot_trials / (ms * 1e-3)
+    launches_per_step = S + 1          # S fused sweep kernels + 1 stand-alone shiftCells per pmc_sweep call
+    n_sweeps_timed = args.steps * S
+
+    # invariants after the timed region (cheap, device side)
+    chk = mc.check(disk, n)
+    chk_t = torch.tensor([chk["total"], chk["out_of_cell"], chk["overlaps"]], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(chk_t, op=dist.ReduceOp.SUM)
+    total_particles = int(chk_t[0].item())
+
+    # roofline of the dominant kernel (the fused sweep kernel, one launch per sweep)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ms_per_launch = ms / n_sweeps_timed          # upper bound: includes 1 stand-alone shift per step
+    alg_bytes = algorithmic_bytes_per_sweep(N, g.n_cells) / n_ranks      # per launch per GPU
+    achieved = alg_bytes / (ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "sweep_tile_kernel<4,32,384,2>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_per_move": alg_bytes * n_ranks / (tot_trials / n_sweeps_timed),
+                "ms_per_launch": ms_per_launch,
+                "issue_ceiling_lane_instr_per_s": 148 * 128 * 1.965e9}
+
+    # end to end through the C-ABI with host buffers (single GPU only: slabs keep state on device)
+    e2e = None
+    if not args.no_e2e and n_ranks == 1:
+        del disk, n
+        torch.cuda.empty_cache()
+        r_host = mc.init_r().cpu().pin_memory()
+        disk_host = torch.empty((g.local_cells, 2, NMAX), dtype=torch.float32).pin_memory()
+        n_host = torch.empty((g.local_cells,), dtype=torch.int16).pin_memory()
+        mc.set_blocking(1)
+        for _ in range(2):
+            mc.run_host(r_host, 0, S, disk_host, n_host)
+        mc.reset_counters()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            mc.run_host(r_host, 0, S, disk_host, n_host)
+        f1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ce = mc.counters()
+        e2e_ms = max(f0.elapsed_time(f1), wall * 1e3)
+        e2e = {"value": ce["trials"] / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(r_host.numel() * 4),
+               "d2h_bytes_per_step": int(disk_host.numel() * 4 + n_host.numel() * 2),
+               "ms_per_step": e2e_ms / args.steps,
+               "what": "pmc_run_host: H2D(r) + assign + sweeps + D2H(disk, n), pinned host buffers",
+               "n_sum_check": int(n_host.to(torch.int64).sum().item())}
+    elif n_ranks > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "what": "not measured for slab runs (state stays on the GPUs between sweeps)"}
+
+    cpu = None
+    if rank == 0 and n_ranks == 1 and not args.no_cpu_baseline:
+        sample_wl = workload if N <= 2 ** 24 else "n16m_phi0.70"
+        v, threads, dt, _ = cpu_baseline(sample_wl, args.cpu_sweeps)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample_wl}: {args.cpu_sweeps} sweeps from the lattice start in {dt:.1f} s; "
+                         "oracle/pmc_oracle.c (the reference has no CPU path), OpenMP over same-colour cells"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_ranks, "steps": args.steps,
+            "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if n_ranks > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "n_particles": N, "phi": phi, "cells_per_side": g.cps,
+                       "cell_w": g.w, "nmax": NMAX, "n_M": N_M, "move_delta": delta,
+                       "proposal": "uniform square", "sweeps_per_step": S, "burn_in_sweeps": args.burn_in,
+                       "init": "square lattice (init_r) + burn-in", "seed": SEED,
+                       "l2": "state (%.0f MB per GPU) larger than L2, no flush" % (g.local_cells * 66 / 1e6),
+                       "parallelism": "1 GPU" if n_ranks == 1 else f"{n_ranks} slabs of {g.rows} cell rows, NCCL ghost-row ring"},
+            "acceptance": tot_acc / tot_trials, "trials": tot_trials, "lost": tot_lost, "status": int(status),
+            "invariants": {"particles": total_particles, "out_of_cell": int(chk_t[1].item()),
+                           "overlaps_below_sigma": int(chk_t[2].item()), "min_d2": chk["min_d2"]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(args.steps * launches_per_step),
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
