@@ -219,27 +219,37 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
     int cnt = n[cell];
     if (cnt == 0) return;                                 /* subsweep.h:252-254 */
     float *X = disk + cell * 2 * nm, *Y = X + nm;         /* cpy_to_Dsh subsweep.h:18-27 */
-    int perm[8] = { 0, 1, 2, 3, 4, 5, 6, 7 };
-    uint32_t rnd[4] = { 0, 0, 0, 0 };
+    /* all random words of this cell's sub-sweep: one Philox call feeds two trials */
+    uint32_t words[2 * 64 + 4];
+    for (int c = 0; c < (g->n_M + 1) / 2; c++)
+        trial_rng(g, (uint32_t)cell, sweep, (uint32_t)c, words + 4 * c);
+    /* random_shuffle subsweep.h:50-58 as intended: a physical Fisher-Yates shuffle of the
+     * cell's slots, written back with the cell like the reference's D_sh.  Only the first
+     * min(n_M, cnt) positions are ever visited by the trial loop, so the shuffle stops there
+     * (partial Fisher-Yates: positions 0..k-1 hold a uniform ordered sample).  Step s takes
+     * its 16 random bits from the low bytes of trial s's two words. */
+    int steps = g->n_M < cnt ? g->n_M : cnt;
+    for (int s = 0; s < steps; s++) {
+        uint32_t ra = words[2 * s], rb = words[2 * s + 1];
+        uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
+        int j = s + (int)((b16 * (uint32_t)(cnt - s)) >> 16);
+        float t;
+        t = X[s]; X[s] = X[j]; X[j] = t;
+        t = Y[s]; Y[s] = Y[j]; Y[j] = t;
+    }
     for (int s = 0; s < g->n_M; s++) {                    /* subsweep.h:279 */
-        if ((s & 1) == 0) trial_rng(g, (uint32_t)cell, sweep, (uint32_t)(s >> 1), rnd);
-        uint32_t ra = (s & 1) ? rnd[2] : rnd[0];
-        uint32_t rb = (s & 1) ? rnd[3] : rnd[1];
-        /* random_shuffle subsweep.h:50-58 as intended (uniform Fisher-Yates), done lazily:
-         * step s of the shuffle happens right before trial s; once all cnt positions are
-         * fixed the order is reused cyclically (i = (i+1) mod atom_counts, subsweep.h:291-296) */
-        if (s < cnt) {
-            uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
-            int j = s + (int)((b16 * (uint32_t)(cnt - s)) >> 16);
-            int t = perm[s]; perm[s] = perm[j]; perm[j] = t;
-        }
-        int slot = perm[s % cnt];
+        uint32_t ra = words[2 * s], rb = words[2 * s + 1];
+        int slot = s % cnt;                               /* i = (i+1) mod atom_counts, subsweep.h:291-296 */
         /* make_move subsweep.h:60-71; proposal = uniform in the square:
-         * odd integer in (-2^24, 2^24) times delta*2^-24 -> exactly symmetric set */
-        int mx = (int)(((ra >> 8) << 1) | 1u) - (1 << 24);
-        int my = (int)(((rb >> 8) << 1) | 1u) - (1 << 24);
-        float px = X[slot] + (float)mx * g->dscale;
-        float py = Y[slot] + (float)my * g->dscale;
+         * +-(odd integer < 2^24) times delta*2^-24: an exactly symmetric set of 2^24 values per
+         * axis; sign = top random bit, magnitude = next 23 bits; one fused rounding per axis */
+        uint32_t ta = ra >> 8, tb = rb >> 8;
+        float fmx = (float)(int)(2u * (ta & 0x7FFFFFu) + 1u);
+        float fmy = (float)(int)(2u * (tb & 0x7FFFFFu) + 1u);
+        if (ta & 0x800000u) fmx = -fmx;
+        if (tb & 0x800000u) fmy = -fmy;
+        float px = fmaf(fmx, g->dscale, X[slot]);
+        float py = fmaf(fmy, g->dscale, Y[slot]);
         (*trials)++;
         /* out_of_bound subsweep.h:73-88 (half-open like assign/shiftCells) */
         if (!(px > 0.0f && px <= w && py > 0.0f && py <= w)) continue;

@@ -313,6 +313,8 @@ int pmc_subsweep(pmc_handle *h, float *d_disk, int16_t *d_n, const int off[2], u
     SweepArgs a;
     memset(&a, 0, sizeof(a));
     a.offx[0] = off[0]; a.offy[0] = off[1];
+    a.offmask = (unsigned)off[0] | ((unsigned)off[1] << 1);
+    a.sanitize_in = 1;
     a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
     CK(pmc_launch_subsweep(h->g, (float4 *)d_disk, d_n, a, h->d_ctr, h->stream));
     int rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
@@ -358,9 +360,12 @@ int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n
             int off[2];
             pmc_colour_to_off(order[k], off);
             a.offx[k] = off[0]; a.offy[k] = off[1];
+            a.offmask |= ((unsigned)off[0] | ((unsigned)off[1] << 1)) << (2 * k);
         }
         a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
         a.shift_on = pend_on; a.shift_f = pend_f; a.shift_d = pend_d;
+        a.sanitize_in = (t == 0);       // only the first kernel reads the caller's arrays
+        { const char *dbg = getenv("PMC_DBG_SKIP"); a.dbg_skip = dbg ? atoi(dbg) : 0; }
         CK(pmc_launch_fused_sweep(h->g, cur_d, cur_n, oth_d, oth_n, a, h->d_ctr, h->stream));
         rc = exchange_ghosts_async(h, oth_d, oth_n);
         if (rc) return rc;

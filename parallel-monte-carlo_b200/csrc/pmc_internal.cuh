@@ -39,10 +39,13 @@ struct Counters {           // device-resident, one per handle
 
 struct SweepArgs {
     int offx[4], offy[4];   // colour offsets in execution order (itoa start.cu:153-157)
+    unsigned offmask;       // the same, packed: bit 2k = offx[k], bit 2k+1 = offy[k]
     unsigned sweep_lo, sweep_hi;
-    int shift_on;           // apply a pending shiftCells(f, d) while loading
+    int sanitize_in;        // input comes from the caller: unused slots may hold garbage
+    int shift_on;           // apply a pending shiftCells(f, d) while staging the tile
     int shift_f;
     float shift_d;
+    int dbg_skip;           // profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store
 };
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`)

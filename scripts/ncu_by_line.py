@@ -40,5 +40,5 @@ for r, loc in zip(data, per_inst):
     a[0] += int(r[ie]); a[1] += int(r[it]); a[2] += int(r[iss]); a[3] += int(r[iw])
 tot = sum(a[0] for a in agg.values()); ts = sum(a[2] for a in agg.values())
 print(f"{'line':28s} {'warp inst':>12s} {'%':>6s} {'samples%':>8s} {'smem wf':>10s}")
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:60]:
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[4]) if len(sys.argv) > 4 else 60]:
     print(f"{str(loc):28s} {a[0]:12d} {100*a[0]/tot:6.1f} {100*a[2]/max(ts,1):8.1f} {a[3]:10d}")

@@ -19,9 +19,9 @@ def run(N, phi, sweeps, delta=0.1, n_M=4):
     ms = e0.elapsed_time(e1)
     c = mc.counters()
     print(f"N={N} phi={phi} cps={mc.geom.cps} sweeps={sweeps} ms/sweep={ms/sweeps:.3f} "
-          f"moves/s={c['trials']/ms*1e3:.3e} acc={c['accepted']/c['trials']:.3f} status={c['status']}", flush=True)
+          f"moves/s={c['trials']/ms*1e3:.3e} acc={c['accepted']/max(c['trials'],1):.3f} status={c['status']}", flush=True)
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("PMC_NOMAIN"):
     run(2**20, 0.70, 50)
     run(2**24, 0.70, 20)
     run(2**22, 0.30, 20, delta=0.4)
