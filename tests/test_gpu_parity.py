@@ -247,3 +247,30 @@ def test_full_size_invariants(N, phi, sweeps):
     mc.sweep(d2, n2, 0, sweeps)
     import torch
     assert torch.equal(disk.view(torch.int32), d2.view(torch.int32)) and torch.equal(n, n2)
+
+
+# ---------------------------------------------------------------- CUDA path vs the reference's OWN kernels
+@pytest.mark.parametrize("seed", [1, 2, 3, 7])
+def test_assign_and_shift_cells_match_the_reference_kernels_on_gpu(seed):
+    """pmc_assign / pmc_shift_cells against what the reference's unmodified assign
+    (kernel.cu:92-150) and V2 shiftCells (shiftCells.h:23-112) computed (tests/golden/
+    ref_kernels_seed*.json, generated by oracle/ref_harness.cu on a B200)."""
+    import json
+    import os
+    import torch
+    import pmc_b200
+    from test_oracle_cpu import _assert_matches_reference_step, _reference_geometry_oracle
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", f"ref_kernels_seed{seed}.json")))
+    p = gold["params"]
+    o = _reference_geometry_oracle(p["n_real"])
+    mc = pmc_b200.ParallelMC(p["n_real"], phi=float(o.phi), sigma_d=1.0, cell_w=2.5, nmax=8, n_M=4,
+                             move_delta=0.1, seed=1)
+    assert mc.geom.cps == 4 and mc.geom.w == 2.5 and mc.geom.L == 10.0
+    r = torch.tensor(np.array(gold["r"], dtype=np.float32)[:2].copy(), device="cuda")
+    disk, n = mc.assign(r)
+    _assert_matches_reference_step(o, disk.cpu().numpy(), n.cpu().numpy(), gold["steps"][0])
+    assert mc.counters()["lost"] == p["n_real"] - sum(gold["steps"][0]["n"])
+    for step in gold["steps"][1:]:
+        mc.shift_cells(disk, n, step["f"], float(np.float32(step["d"])))
+        _assert_matches_reference_step(o, disk.cpu().numpy(), n.cpu().numpy(), step)
