@@ -79,6 +79,12 @@ struct pmc_handle {
     int16_t *run_n;
     // slab ring
     ncclComm_t comm;
+    // fast fused sweep (pmc_sweep4.cu): internal-layout ping-pong buffers + their TMA descriptors
+    int v4_ok;                  // parameters qualify (n_M == 4, w >= 2 sigma, cps >= 48)
+    int v4_padded;              // both buffers hold valid cells everywhere (padding included)
+    Geom4 g4;
+    float4 *v4_buf[2];
+    alignas(64) unsigned char v4_tmap[2][128];
 };
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
@@ -170,6 +176,18 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
     pg.row0 = g.row0; pg.rows = g.rows; pg.ghost_rows = g.ghost;
     pg.local_cells = (long long)g.local_rows * g.cps;
 
+    {   // fast path eligibility: the 3-neighbour-cell argument needs w >= 2 sigma with a margin
+        // far above float rounding; tiny boxes would need more than one periodic image
+        Geom4 &q = h->g4;
+        q.cps = g.cps; q.row0 = g.row0; q.rows = g.rows; q.wrap_y = g.wrap_y;
+        pmc4_alloc_shape(g.cps, g.rows, &q.CH, &q.ROWS);
+        q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale;
+        q.seed_lo = g.seed_lo; q.seed_hi = g.seed_hi;
+        h->v4_ok = (p.n_M == 4) && ((double)g.w >= 2.0 * (double)p.sigma_d * (1.0 + 1e-5)) && g.cps >= 48 &&
+                   g.rows >= 2 * kMY && (p.n_ranks == 1 || kGhostRows == kMY);
+        const char *force = getenv("PMC_FORCE_GENERIC");
+        if (force && atoi(force)) h->v4_ok = 0;
+    }
     if (p.device >= 0) { cudaError_t e = cudaSetDevice(p.device); if (e != cudaSuccess) { free(h); return (int)e; } }
     cudaError_t e = cudaGetDevice(&h->device);
     if (e != cudaSuccess) { free(h); return (int)e; }
@@ -194,6 +212,7 @@ int pmc_destroy(pmc_handle *h)
     cudaFree(h->d_ctr); cudaFree(h->scratch_disk); cudaFree(h->scratch_n);
     cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
     cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
+    cudaFree(h->v4_buf[0]); cudaFree(h->v4_buf[1]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     free(h);
     return 0;
@@ -336,6 +355,71 @@ int pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
     return finish(h);
 }
 
+static size_t v4_bytes(const pmc_handle *h) { return (size_t)2 * h->g4.CH * h->g4.ROWS * 4 * sizeof(float4); }
+
+// slab ring on the internal layout: whole rows (4 planes x 2 parities x CH chunks) are contiguous
+static int v4_exchange_async(pmc_handle *h, float4 *buf)
+{
+    if (h->p.n_ranks <= 1) return 0;
+    if (!h->comm) return PMC_E_COMM;
+    const int R = h->p.n_ranks, rows = h->g4.rows;
+    const int lower = (h->p.rank + R - 1) % R, upper = (h->p.rank + 1) % R;
+    const size_t rp = (size_t)h->g4.CH * 128, blk = (size_t)kMY * rp;
+    char *B = (char *)buf;
+    int rc = 0;
+    rc |= g_nccl.GroupStart();
+    rc |= g_nccl.Send(B + (size_t)kMY * rp, blk, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.Send(B + (size_t)rows * rp, blk, ncclInt8, upper, h->comm, h->stream);
+    rc |= g_nccl.Recv(B + (size_t)(kMY + rows) * rp, blk, ncclInt8, upper, h->comm, h->stream);
+    rc |= g_nccl.Recv(B, blk, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.GroupEnd();
+    return rc ? PMC_E_COMM : 0;
+}
+
+// start.cu:237-260 on the fast path: caller layout -> internal layout, n_sweeps x ONE kernel
+// (4 colours + this sweep's shiftCells applied while the tile is stored), -> caller layout.
+static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n_sweeps)
+{
+    for (int b = 0; b < 2; b++)
+        if (!h->v4_buf[b]) {
+            CK(cudaMalloc(&h->v4_buf[b], v4_bytes(h)));
+            int rc = pmc4_make_tensor_map(h->v4_tmap[b], h->v4_buf[b], h->g4);
+            if (rc) return rc;
+            h->v4_padded = 0;
+        }
+    const int ghost = h->g.ghost;
+    CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[0], h->stream));
+    if (!h->v4_padded) {        // cells beyond the margins are never written again: make them valid once
+        CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[1], h->stream));
+        h->v4_padded = 1;
+    }
+    int cur = 0;
+    static const int dbg = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
+    for (int t = 0; t < n_sweeps; t++) {
+        const uint64_t sweep = sweep0 + (uint64_t)t;
+        int order[4], f;
+        float d;
+        pmc_schedule(h, sweep, order, &f, &d);
+        SweepArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int k = 0; k < 4; k++) {
+            int off[2];
+            pmc_colour_to_off(order[k], off);
+            a.offx[k] = off[0]; a.offy[k] = off[1];
+            a.offmask |= ((unsigned)off[0] | ((unsigned)off[1] << 1)) << (2 * k);
+        }
+        a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
+        a.shift_on = 1; a.shift_f = f; a.shift_d = d;
+        a.dbg_skip = dbg;
+        CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream));
+        int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1]);
+        if (rc) return rc;
+        cur ^= 1;
+    }
+    CK(pmc4_launch_export(h->g4, ghost, h->v4_buf[cur], (float4 *)d_disk, d_n, h->stream));
+    return finish(h);
+}
+
 // start.cu:237-260, n_sweeps times.  Sweep t runs as ONE kernel that first applies the shift
 // drawn at the end of sweep t-1 (while staging its tile) and then the four colours; the last
 // shift is materialised by the stand-alone kernel so the caller's arrays are complete.
@@ -343,6 +427,7 @@ int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n
 {
     if (!h || !d_disk || !d_n || n_sweeps < 0) return PMC_E_INVALID;
     if (n_sweeps == 0) return 0;
+    if (h->v4_ok) return sweep_v4(h, d_disk, d_n, sweep0, n_sweeps);
     int rc = ensure_scratch(h);
     if (rc) return rc;
     float4 *cur_d = (float4 *)d_disk, *oth_d = h->scratch_disk;

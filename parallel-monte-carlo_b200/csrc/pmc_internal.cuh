@@ -66,6 +66,24 @@ cudaError_t pmc_launch_gr_hist(const DevGeom &g, const float4 *disk, const int16
                                float r_max, int nbins, unsigned long long *hist, cudaStream_t st);
 int pmc_fused_launch_count();   // kernels per fused sweep (for bench gpu_launches)
 
+// ---- fast fused sweep on the handle-owned internal layout (pmc_sweep4.cu)
+constexpr int kMX = 6, kMY = 5; // margin columns (even) / rows holding periodic images or slab ghosts
+struct Geom4 {
+    int cps, row0, rows, wrap_y;
+    int CH;                     // float4 chunks per (row, plane, parity) run
+    int ROWS;                   // allocated rows
+    float w, hw, sigma2, dscale;
+    unsigned seed_lo, seed_hi;
+};
+int pmc4_tile_x();
+int pmc4_tile_y();
+void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS);
+int pmc4_make_tensor_map(void *tmap_out128, const float4 *base, const Geom4 &g);
+cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out, cudaStream_t st);
+cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, float4 *disk, int16_t *n, cudaStream_t st);
+cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
+                              Counters *ctr, cudaStream_t st);
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ Philox4x32-10
 // Salmon et al., SC'11.  Counter = {cell id, sweep lo, sweep hi, call}, key = seed.
