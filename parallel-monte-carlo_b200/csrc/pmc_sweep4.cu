@@ -175,7 +175,8 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
 #pragma unroll
         for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, &tmap, 4 * ((X0 - xs) >> 1), 0, p, Y0, mbar);
     }
-    __syncthreads();            // the barrier word is initialised before anyone polls it
+    if (tid == 0) mbar_wait(mbar, 0);   // one poller; the others observe the completed phase once
+    __syncthreads();
     mbar_wait(mbar, 0);
 
     // ------------------------------------------------------------ the four sub-sweeps
@@ -208,7 +209,7 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
                 // hold a disk closer than sigma (w >= 2 sigma), or -1 when the proposal leaves the
                 // cell (out_of_bound subsweep.h:73-88)
                 auto neighbours_min_d2 = [&](const float px, const float py) -> float {
-                    if (!(px > 0.0f && px <= w && py > 0.0f && py <= w)) return -1.0f;
+                    const bool inb = px > 0.0f && px <= w && py > 0.0f && py <= w;
                     const bool goL = px <= hw, goD = py <= hw;
                     const float npxs = -__fadd_rn(px, goL ? w : -w);     // -(px - helper*w), subsweep.h:139-151
                     const float npys = -__fadd_rn(py, goD ? w : -w);
@@ -217,7 +218,7 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
                     float m = cell_min_d2<PLC>(pH, npxs, -py);
                     m = fminf(m, cell_min_d2<PLC>(pown + dV, -px, npys));
                     m = fminf(m, cell_min_d2<PLC>(pH + dV, npxs, npys));
-                    return m;
+                    return inb ? m : -1.0f;      // out of the cell: rejected whatever the neighbours say
                 };
 
                 float ox[8] = { x03.x, x03.y, x03.z, x03.w, x47.x, x47.y, x47.z, x47.w };
@@ -323,29 +324,30 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
             load_cell(i0 + len * di, j0 + len * dj, edge);
         }
         __syncthreads();
-#pragma unroll 1
-        for (int u = 0; u < len; u++) {
-            const int i = i0 + u * di, j = j0 + u * dj;
-            CellRegs up;
-            if (u + 1 < len) load_cell(i + di, j + dj, up);
-            else up = edge;
-            const CellRegs nxt = up;
-            float4 *p = cell_ptr(i, j);
-            p[0] = make_float4(kSent, kSent, kSent, kSent);
-            p[PLC] = make_float4(kSent, kSent, kSent, kSent);
-            p[2 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
-            p[3 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float *fx = reinterpret_cast<float *>(p);
-            int dropped, nNew;
-            if (a.shift_f == 0) nNew = shift_into_tile<0, PLC>(cur, up, d, w, sshift, fx, &dropped);
-            else nNew = shift_into_tile<1, PLC>(cur, up, d, w, sshift, fx, &dropped);
-            if (nNew < PMC_NMAX) fx[3 * PLC * 4 + 3] = __int_as_float(nNew);
-            if (dropped) {
-                atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
-                if ((unsigned)(i - ox0) < (unsigned)nox && (unsigned)(j - oy0) < (unsigned)noy)
-                    atomicAdd(&ctr->lost, (unsigned long long)dropped);
+        constexpr int KMAX = K0 > K1 ? K0 : K1;
+#pragma unroll
+        for (int u = 0; u < KMAX; u++) {
+            if (u < len) {
+                const int i = i0 + u * di, j = j0 + u * dj;
+                CellRegs up = edge;
+                if (u + 1 < len) load_cell(i + di, j + dj, up);
+                float4 *p = cell_ptr(i, j);
+                p[0] = make_float4(kSent, kSent, kSent, kSent);
+                p[PLC] = make_float4(kSent, kSent, kSent, kSent);
+                p[2 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
+                p[3 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float *fx = reinterpret_cast<float *>(p);
+                int dropped, nNew;
+                if (a.shift_f == 0) nNew = shift_into_tile<0, PLC>(cur, up, d, w, sshift, fx, &dropped);
+                else nNew = shift_into_tile<1, PLC>(cur, up, d, w, sshift, fx, &dropped);
+                if (nNew < PMC_NMAX) fx[3 * PLC * 4 + 3] = __int_as_float(nNew);
+                if (dropped) {
+                    atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
+                    if ((unsigned)(i - ox0) < (unsigned)nox && (unsigned)(j - oy0) < (unsigned)noy)
+                        atomicAdd(&ctr->lost, (unsigned long long)dropped);
+                }
+                cur = up;
             }
-            cur = nxt;
         }
         __syncthreads();
     }
@@ -358,27 +360,37 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         static_assert(THREADS % (8 * HX) == 0, "store mapping");
         const int h = tid % HX, pr = (tid / HX) & 1, pl = (tid / (2 * HX)) & 3, rg = tid / (8 * HX);
         const int ox = 2 * h + pr;                                  // owned column (parity == internal column parity)
-        const int ux = blockIdx.x * TX + ox;
+        const int ux = blockIdx.x * TX + ox, uy0 = blockIdx.y * TY;
         if (ox < nox) {
             const int is = ox0 + ox + xs;
-            const float4 *src = sm + pl * PLC + (is & 1) * HB + (is >> 1);
-            const long long colc = (long long)pr * g.CH + ((kMX + ux) >> 1);
+            const float4 *src = sm + pl * PLC + (is & 1) * HB + (is >> 1) + (oy0 + rg) * PITCH;
+            const long long rstride = (long long)8 * g.CH;          // float4 chunks per internal row
+            float4 *dst = dout + ((long long)(kMY + uy0 + rg) * 4 + pl) * 2 * g.CH + (long long)pr * g.CH + ((kMX + ux) >> 1);
             // periodic image of this column inside the margins (cps is even: parity is kept)
             const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);
+            const bool yedge = g.wrap_y && (uy0 < kMY || uy0 + noy > g.rows - kMY);
+            if (!ximg && !yedge) {
+#pragma unroll 2
+                for (int oyy = rg; oyy < noy; oyy += RSTEP) {
+                    *dst = *src;
+                    src += RSTEP * PITCH; dst += RSTEP * rstride;
+                }
+            } else {
 #pragma unroll 1
-            for (int oyy = rg; oyy < noy; oyy += RSTEP) {
-                const float4 v = src[(oy0 + oyy) * PITCH];
-                const int uy = blockIdx.y * TY + oyy;
-                const long long rowc = ((long long)(kMY + uy) * 4 + pl) * 2 * g.CH;
-                dout[rowc + colc] = v;
-                if (ximg) dout[rowc + colc + ximg] = v;
-                if (g.wrap_y) {
-                    const int yimg = uy < kMY ? g.rows : (uy >= g.rows - kMY ? -g.rows : 0);
-                    if (yimg) {
-                        const long long rowi = ((long long)(kMY + uy + yimg) * 4 + pl) * 2 * g.CH;
-                        dout[rowi + colc] = v;
-                        if (ximg) dout[rowi + colc + ximg] = v;
+                for (int oyy = rg; oyy < noy; oyy += RSTEP) {
+                    const float4 v = *src;
+                    const int uy = uy0 + oyy;
+                    dst[0] = v;
+                    if (ximg) dst[ximg] = v;
+                    if (g.wrap_y) {
+                        const int yimg = uy < kMY ? g.rows : (uy >= g.rows - kMY ? -g.rows : 0);
+                        if (yimg) {
+                            float4 *di = dst + (long long)yimg * rstride;
+                            di[0] = v;
+                            if (ximg) di[ximg] = v;
+                        }
                     }
+                    src += RSTEP * PITCH; dst += RSTEP * rstride;
                 }
             }
         }
