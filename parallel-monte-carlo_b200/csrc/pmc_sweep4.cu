@@ -3,21 +3,24 @@
 // This is the throughput path behind pmc_sweep(); pmc_sweep.cu keeps the generic kernel
 // (any n_M, w < 2 sigma, tiny boxes, the single-colour call site).
 //
-// Differences from the generic kernel, all chosen to cut issued instructions per trial:
-//   * INTERNAL STATE LAYOUT (handle-owned, never seen by the caller): float4 chunks
-//         chunk(X, Y, plane) = ((Y*4 + plane)*2 + (X & 1)) * CH + (X >> 1)
-//     planes = x slots 0-3, x slots 4-7, y slots 0-3, y slots 4-7; even and odd columns are
-//     split so that the same-colour cells a warp works on are contiguous (conflict-free
-//     LDS.128) and so that ONE 4-D TMA box per plane lands a tile in shared memory in
-//     exactly the layout the sub-sweeps read: no per-cell index arithmetic at all.
+// Differences from the generic kernel, chosen to cut issued instructions AND shared-memory
+// wavefronts per trial (ncu: the LSU data pipe is the tightest resource of this path):
+//   * INTERNAL STATE LAYOUT (handle-owned, never seen by the caller): one cell = 4 float4
+//     chunks   P0 = x0..x3   P1 = y0..y3   P2 = x4 x5 y4 y5   P3 = x6 x7 y6 y7
+//         chunk(X, Y, P) = ((Y*4 + P)*2 + (X & 1)) * CH + (X >> 1)
+//     Even and odd columns are split so that the same-colour cells a warp works on are
+//     contiguous (conflict-free LDS.128) and ONE 4-D TMA box per plane lands a tile in
+//     shared memory in exactly the layout the sub-sweeps read: no index arithmetic at all.
 //     The box is surrounded by margins (kMX columns, kMY rows) holding periodic images, written
 //     by the CTA that produces the original cell (single GPU) or by the NCCL ring (slab rows),
 //     so a tile never wraps.
-//   * the cell count lives in-band: unused slots have x = sentinel; when a cell holds fewer
-//     than 8 particles the bits of its y[7] are the count.  No count array on the hot path.
+//   * cells hold <= 6 disks in all but ~1e-5 of the cases at phi = 0.70, w = 2 sigma: a tile
+//     whose staged cells all hold <= 6 runs the NS = 6 instantiation, which never touches P3
+//     (3 instead of 4 chunks per neighbour cell, 24 instead of 32 pair tests per trial).
+//   * the cell count lives in-band: unused slots have x = sentinel; a cell with fewer than 8
+//     (6) disks carries its count in the bits of y7 (y5).  No count array on the hot path.
 //   * the grid shift of THIS sweep is applied while the tile leaves shared memory (the tile
-//     carries one extra upstream row / column), so only owned cells are re-binned (the
-//     generic kernel re-bins its whole halo while staging).
+//     carries one extra upstream row / column), so only owned cells are re-binned.
 //   * neighbour cells needed by a trial: with w >= 2 sigma a proposal in the left half of its
 //     cell can only touch the left column of neighbours, etc.: one compare per axis.
 // Every random number is a pure function of (seed, sweep, global cell id, trial), so the
@@ -72,7 +75,9 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ int decode_cnt(float x7, float y7) { return x7 < kSentTest ? 8 : __float_as_int(y7); }
+// in-band count: y7 when fewer than 8 disks (P3 = x6 x7 y6 y7), y5 when fewer than 6 (P2 = x4 x5 y4 y5)
+__device__ __forceinline__ int decode_cnt8(const float4 &p3) { return p3.y < kSentTest ? 8 : __float_as_int(p3.w); }
+__device__ __forceinline__ int decode_cnt6(const float4 &p2) { return p2.y < kSentTest ? 6 : __float_as_int(p2.w); }
 
 // two slots per instruction (Blackwell packed FP32): d2 = (q.x + npx)^2 + (q.y + npy)^2, the
 // oracle's fmaf(dx, dx, dy*dy) with dx = pxs - qx (sign is irrelevant after squaring)
@@ -83,16 +88,23 @@ __device__ __forceinline__ float2 pair2(float qx0, float qx1, float qy0, float q
     return __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
 }
 
-template <int PLC>
+// smallest squared distance between the trial point (negated, in this cell's frame) and the
+// first NS slots of one staged cell; unused slots hold the sentinel
+template <int NS, int PLC>
 __device__ __forceinline__ float cell_min_d2(const float4 *cp, float npx, float npy)
 {
-    const float4 x03 = cp[0], x47 = cp[PLC], y03 = cp[2 * PLC], y47 = cp[3 * PLC];
+    const float4 p0 = cp[0], p1 = cp[PLC], p2 = cp[2 * PLC];
     const float2 nx = make_float2(npx, npx), ny = make_float2(npy, npy);
-    const float2 a = pair2(x03.x, x03.y, y03.x, y03.y, nx, ny);
-    const float2 b = pair2(x03.z, x03.w, y03.z, y03.w, nx, ny);
-    const float2 c = pair2(x47.x, x47.y, y47.x, y47.y, nx, ny);
-    const float2 e = pair2(x47.z, x47.w, y47.z, y47.w, nx, ny);
-    return fminf(fminf(fminf(a.x, a.y), fminf(b.x, b.y)), fminf(fminf(c.x, c.y), fminf(e.x, e.y)));
+    const float2 a = pair2(p0.x, p0.y, p1.x, p1.y, nx, ny);
+    const float2 b = pair2(p0.z, p0.w, p1.z, p1.w, nx, ny);
+    const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
+    float m = fminf(fminf(fminf(a.x, a.y), fminf(b.x, b.y)), fminf(c.x, c.y));
+    if (NS == 8) {
+        const float4 p3 = cp[3 * PLC];
+        const float2 e = pair2(p3.x, p3.y, p3.z, p3.w, nx, ny);
+        m = fminf(m, fminf(e.x, e.y));
+    }
+    return m;
 }
 
 // +-(odd integer < 2^24) as a float without I2F: 0x4B800000 | m23 is the float 2^24 + 2*m23
@@ -103,9 +115,11 @@ __device__ __forceinline__ float signed_odd24(uint32_t r)
     return __uint_as_float(__float_as_uint(mag) | (r & 0x80000000u));
 }
 
-// V2 shiftCells.h:23-112 for one destination cell, written into the staged tile in place.
-// fx points at x slot 0 of the destination cell.
-template <int F, int PLC>
+// V2 shiftCells.h:23-112 for one destination cell.  The result is written in place into the
+// staged tile in the PLAIN plane order (x0-3 | x4-7 | y0-3 | y4-7: slot -> address is one
+// shift and one multiply-add); the store phase converts to P0..P3 on the way out.
+// fx points at the first float of the destination cell's first chunk.
+template <int NS, int F, int PLC>
 __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRegs &up, float d, float w,
                                                float sshift, float *fx, int *dropped)
 {
@@ -114,7 +128,7 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
     constexpr int OFF = F == 0 ? 2 * PF : -2 * PF;      // to the other coordinate
     int n = 0, drop = 0;
 #pragma unroll
-    for (int i = 0; i < PMC_NMAX; i++) {
+    for (int i = 0; i < NS; i++) {
         const float fc = F == 0 ? f4get(own.x03, own.x47, i) : f4get(own.y03, own.y47, i);
         const float oc = F == 0 ? f4get(own.y03, own.y47, i) : f4get(own.x03, own.x47, i);
         const float D = __fadd_rn(fc, -d);
@@ -126,7 +140,7 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
         }
     }
 #pragma unroll
-    for (int i = 0; i < PMC_NMAX; i++) {
+    for (int i = 0; i < NS; i++) {
         const float fc = F == 0 ? f4get(up.x03, up.x47, i) : f4get(up.y03, up.y47, i);
         const float oc = F == 0 ? f4get(up.y03, up.y47, i) : f4get(up.x03, up.x47, i);
         const float D = __fadd_rn(fc, -d);
@@ -142,6 +156,204 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
     return n;
 }
 
+// everything one CTA knows about its tile
+struct TileCtx {
+    int RX, RY;             // region the sub-sweeps work on (owned + halo + the extra upstream strip)
+    int rx0, ry0;           // unwrapped global column / owned-relative row of region (0, 0)
+    int xs;                 // region column i is staged column i + xs
+    int ox0, oy0;           // region coordinates of the owned tile's corner
+    int nox, noy;           // owned extent after clipping at the box / slab edge
+};
+
+// ---- one colour: one thread per active cell (subsweep.h:242-245), own cell in registers
+template <int NS, int TX, int TY>
+__device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
+                                            int k, int aq, int bq, unsigned &my_trials, unsigned &my_acc)
+{
+    using TL = Tile4<TX, TY>;
+    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
+    const int cps = g.cps;
+    const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
+    const int lo = k + 1;                       // cells closer than lo to the region edge are stale
+    const int pi = ((int)((a.offmask >> (2 * k)) & 1u) - t.rx0) & 1;       // region-column parity of the active colour
+    const int pj = ((int)((a.offmask >> (2 * k + 1)) & 1u) - (g.row0 + t.ry0)) & 1;
+    const int i = lo + ((pi - lo) & 1) + 2 * aq, j = lo + ((pj - lo) & 1) + 2 * bq;
+    if (!(i < t.RX - lo && j < t.RY - lo)) return;
+    const int is = i + t.xs, par = is & 1;
+    float4 *pown = sm + j * PITCH + par * HB + (is >> 1);
+    const float4 *pL = sm + j * PITCH + (1 - par) * HB + ((is - 1) >> 1);      // left neighbour; right = pL + 1
+    const float4 p0 = pown[0], p1 = pown[PLC], p2 = pown[2 * PLC];
+    float4 p3 = make_float4(kSent, kSent, 0.f, 0.f);
+    if (NS == 8) p3 = pown[3 * PLC];
+    const int cnt = NS == 8 ? decode_cnt8(p3) : decode_cnt6(p2);
+    if (cnt == 0) return;                       // subsweep.h:252-254
+    const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
+    int gx = t.rx0 + i, gy = g.row0 + t.ry0 + j;
+    gx += gx < 0 ? cps : 0; gx -= gx >= cps ? cps : 0;
+    gy += gy < 0 ? cps : 0; gy -= gy >= cps ? cps : 0;
+    const uint32_t cell_id = (uint32_t)gy * (uint32_t)cps + (uint32_t)gx;
+
+    // neighbour part of one trial: smallest d2 against the 3 neighbour cells that can hold a
+    // disk closer than sigma (w >= 2 sigma), or -1 when the proposal leaves the cell
+    // (out_of_bound subsweep.h:73-88)
+    auto neighbours_min_d2 = [&](const float px, const float py) -> float {
+        const bool inb = px > 0.0f && px <= w && py > 0.0f && py <= w;
+        const bool goL = px <= hw, goD = py <= hw;
+        const float npxs = -__fadd_rn(px, goL ? w : -w);     // -(px - helper*w), subsweep.h:139-151
+        const float npys = -__fadd_rn(py, goD ? w : -w);
+        const float4 *pH = pL + (goL ? 0 : 1);
+        const int dV = goD ? -PITCH : PITCH;
+        float m = cell_min_d2<NS, PLC>(pH, npxs, -py);
+        m = fminf(m, cell_min_d2<NS, PLC>(pown + dV, -px, npys));
+        m = fminf(m, cell_min_d2<NS, PLC>(pH + dV, npxs, npys));
+        return inb ? m : -1.0f;                 // out of the cell: rejected whatever the neighbours say
+    };
+
+    float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
+    float oy[8] = { p1.x, p1.y, p1.z, p1.w, p2.z, p2.w, p3.z, p3.w };
+    uint32_t rw[8];
+    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.seed_lo, g.seed_hi, rw[0], rw[1], rw[2], rw[3]);
+    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.seed_lo, g.seed_hi, rw[4], rw[5], rw[6], rw[7]);
+    // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const uint32_t b16 = ((rw[2 * s] & 0xFFu) << 8) | (rw[2 * s + 1] & 0xFFu);
+        const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
+        const int jj = s + (int)((b16 * (uint32_t)mrem) >> 16);
+        const float tx = ox[s], ty = oy[s];
+        float nx = tx, ny = ty;
+#pragma unroll
+        for (int q = s + 1; q < NS; q++) {
+            const bool p = (jj == q);
+            nx = p ? ox[q] : nx; ny = p ? oy[q] : ny;
+            ox[q] = p ? tx : ox[q]; oy[q] = p ? ty : oy[q];
+        }
+        ox[s] = nx; oy[s] = ny;
+    }
+    // trials 0..3 move slot s mod cnt (subsweep.h:279-297), all register indices static
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const bool cA = cnt > s;                            // slot == s
+        const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
+        const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
+        const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
+        const float px = __fmaf_rn(signed_odd24(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
+        const float py = __fmaf_rn(signed_odd24(rw[2 * s + 1]), dscale, y);
+        my_trials += owned ? 1u : 0u;
+        float m = neighbours_min_d2(px, py);
+        // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
+        const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
+        float2 d01 = pair2(ox[0], ox[1], oy[0], oy[1], npx, npy);
+        float2 d23 = pair2(ox[2], ox[3], oy[2], oy[3], npx, npy);
+        const float2 d45 = pair2(ox[4], ox[5], oy[4], oy[5], npx, npy);
+        const float big = 3.0e38f;
+        if (s == 0) d01.x = big;
+        if (s == 1) { d01.y = cA ? big : d01.y; d01.x = cA ? d01.x : big; }
+        if (s == 2) { d23.x = cA ? big : d23.x; d01.x = cA ? d01.x : big; }
+        if (s == 3) { d23.y = cA ? big : d23.y; d01.y = cB ? big : d01.y; d01.x = (cA | cB) ? d01.x : big; }
+        m = fminf(m, fminf(fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)), fminf(d45.x, d45.y)));
+        if (NS == 8) {
+            const float2 d67 = pair2(ox[6], ox[7], oy[6], oy[7], npx, npy);
+            m = fminf(m, fminf(d67.x, d67.y));
+        }
+        // accept_move subsweep.h:194-217 (hard disks: accept iff in bounds and no overlap)
+        const bool acc = !(m < sigma2);
+        my_acc += (acc && owned) ? 1u : 0u;
+        if (s == 0) { ox[0] = acc ? px : ox[0]; oy[0] = acc ? py : oy[0]; }
+        else {
+            const bool w0 = acc & !cA & !cB, w1 = acc & cB, ws = acc & cA;
+            ox[s] = ws ? px : ox[s]; oy[s] = ws ? py : oy[s];
+            ox[0] = w0 ? px : ox[0]; oy[0] = w0 ? py : oy[0];
+            if (s == 3) { ox[1] = w1 ? px : ox[1]; oy[1] = w1 ? py : oy[1]; }
+        }
+    }
+    // cpy_D_sh_to_Disk subsweep.h:29-36 (shuffled order is written back, like the reference)
+    pown[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
+    pown[PLC] = make_float4(oy[0], oy[1], oy[2], oy[3]);
+    pown[2 * PLC] = make_float4(ox[4], ox[5], oy[4], oy[5]);
+    if (NS == 8) pown[3 * PLC] = make_float4(ox[6], ox[7], oy[6], oy[7]);
+}
+
+// ---- shiftCells(f, d) of this sweep for the owned cells, in place (plain plane order out)
+template <int NS, int TX, int TY>
+__device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const SweepArgs &a, float w, int sdir,
+                                           int tid, Counters *ctr)
+{
+    using TL = Tile4<TX, TY>;
+    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC, THREADS = TL::THREADS;
+    const float d = a.shift_d;
+    const float sshift = __fmul_rn(w, (float)sdir);                 // shiftCells.h:84-86
+    // One thread owns a strip of K consecutive owned cells along the shift axis and walks it
+    // from the downstream end to the upstream end: cell u is rewritten only after raw cell
+    // u+1 has been read.  The raw cell after the strip (next strip, or the extra upstream
+    // row / column) is read before the barrier.
+    constexpr int SEG1 = THREADS / TX, K1 = (TY + SEG1 - 1) / SEG1;     // f = 1: column strips of K1 rows
+    constexpr int SEG0 = THREADS / TY < 8 ? THREADS / TY : 8, K0 = (TX + SEG0 - 1) / SEG0;   // f = 0: row strips of K0 columns
+    int i0, j0, len, di, dj;
+    if (a.shift_f == 1) {
+        const int seg = tid / TX, col = tid - seg * TX, k0 = seg * K1;
+        len = (seg < SEG1 && k0 < TY) ? min(K1, TY - k0) : 0;
+        i0 = t.ox0 + col; j0 = t.oy0 + (sdir > 0 ? k0 : TY - 1 - k0);
+        di = 0; dj = sdir;
+    } else {
+        const int row = tid / SEG0, seg = tid - row * SEG0, k0 = seg * K0;
+        len = (row < TY && k0 < TX) ? min(K0, TX - k0) : 0;
+        j0 = t.oy0 + row; i0 = t.ox0 + (sdir > 0 ? k0 : TX - 1 - k0);
+        di = sdir; dj = 0;
+    }
+    auto cell_ptr = [&](int i, int j) -> float4 * {
+        const int is = i + t.xs;
+        return sm + j * PITCH + (is & 1) * HB + (is >> 1);
+    };
+    auto load_cell = [&](int i, int j, CellRegs &c) {           // P0..P3 -> plain x / y registers
+        const float4 *p = cell_ptr(i, j);
+        const float4 p0 = p[0], p1 = p[PLC], p2 = p[2 * PLC];
+        c.x03 = p0; c.y03 = p1;
+        if (NS == 8) {
+            const float4 p3 = p[3 * PLC];
+            c.x47 = make_float4(p2.x, p2.y, p3.x, p3.y); c.y47 = make_float4(p2.z, p2.w, p3.z, p3.w);
+            c.cnt = decode_cnt8(p3);
+        } else {
+            c.x47 = make_float4(p2.x, p2.y, kSent, kSent); c.y47 = make_float4(p2.z, p2.w, 0.f, 0.f);
+            c.cnt = decode_cnt6(p2);
+        }
+    };
+    CellRegs cur, edge;
+    if (len > 0) {
+        load_cell(i0, j0, cur);
+        load_cell(i0 + len * di, j0 + len * dj, edge);
+    }
+    __syncthreads();
+    constexpr int KMAX = K0 > K1 ? K0 : K1;
+#pragma unroll
+    for (int u = 0; u < KMAX; u++) {
+        if (u < len) {
+            const int i = i0 + u * di, j = j0 + u * dj;
+            CellRegs up = edge;
+            if (u + 1 < len) load_cell(i + di, j + dj, up);
+            float4 *p = cell_ptr(i, j);
+            p[0] = make_float4(kSent, kSent, kSent, kSent);
+            p[PLC] = make_float4(kSent, kSent, kSent, kSent);
+            p[2 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
+            p[3 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float *fx = reinterpret_cast<float *>(p);
+            int dropped, nNew;
+            if (a.shift_f == 0) nNew = shift_into_tile<NS, 0, PLC>(cur, up, d, w, sshift, fx, &dropped);
+            else nNew = shift_into_tile<NS, 1, PLC>(cur, up, d, w, sshift, fx, &dropped);
+            // in-band counts (plain order: y5 = plane 3 word 1, y7 = plane 3 word 3)
+            if (nNew < PMC_NMAX) fx[3 * PLC * 4 + 3] = __int_as_float(nNew);
+            if (nNew < 6) fx[3 * PLC * 4 + 1] = __int_as_float(nNew);
+            if (dropped) {
+                atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
+                if ((unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy)
+                    atomicAdd(&ctr->lost, (unsigned long long)dropped);
+            }
+            cur = up;
+        }
+    }
+    __syncthreads();
+}
+
 template <int TX, int TY, int MINB>
 __global__ void __launch_bounds__(Tile4<TX, TY>::THREADS, MINB)
 sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dout, const Geom4 g,
@@ -154,18 +366,20 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
 
     const int tid = threadIdx.x;
     const int cps = g.cps;
-    const float w = g.w;
 
     // this sweep's grid shift: the tile carries one extra row / column on the upstream side
     const bool do_shift = a.shift_on && !(a.dbg_skip & 2);
     const int sdir = (a.shift_d <= 0.0f) ? -1 : 1;                       // shiftCells.h:38-44
     const int exl = (do_shift && a.shift_f == 0 && sdir < 0), exh = (do_shift && a.shift_f == 0 && sdir > 0);
     const int eyl = (do_shift && a.shift_f == 1 && sdir < 0), eyh = (do_shift && a.shift_f == 1 && sdir > 0);
-    const int RX = TX + 2 * H + exl + exh, RY = TY + 2 * H + eyl + eyh;  // region the sub-sweeps work on
-    const int rx0 = blockIdx.x * TX - H - exl;      // unwrapped global column of region column 0
-    const int ry0 = blockIdx.y * TY - H - eyl;      // owned-relative row of region row 0
-    const int X0 = rx0 + kMX, Y0 = ry0 + kMY;       // the same in internal array coordinates (>= 0)
-    const int xs = X0 & 1;                          // region column i is staged column i + xs
+    TileCtx t;
+    t.RX = TX + 2 * H + exl + exh; t.RY = TY + 2 * H + eyl + eyh;
+    t.rx0 = blockIdx.x * TX - H - exl;
+    t.ry0 = blockIdx.y * TY - H - eyl;
+    const int X0 = t.rx0 + kMX, Y0 = t.ry0 + kMY;   // region (0, 0) in internal array coordinates (>= 0)
+    t.xs = X0 & 1;
+    t.ox0 = H + exl; t.oy0 = H + eyl;
+    t.nox = min(TX, cps - (int)blockIdx.x * TX); t.noy = min(TY, g.rows - (int)blockIdx.y * TY);
 
     // ------------------------------------------------------------ stage the tile: 4 TMA boxes
     if (tid == 0) {
@@ -173,212 +387,84 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(mbar, (unsigned)(4 * TL::PLB * 16));
 #pragma unroll
-        for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, &tmap, 4 * ((X0 - xs) >> 1), 0, p, Y0, mbar);
+        for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, &tmap, 4 * ((X0 - t.xs) >> 1), 0, p, Y0, mbar);
+        mbar_wait(mbar, 0);     // one poller; the others observe the completed phase once
     }
-    if (tid == 0) mbar_wait(mbar, 0);   // one poller; the others observe the completed phase once
     __syncthreads();
     mbar_wait(mbar, 0);
 
+    // does any staged cell hold 7 or 8 disks (x6 in use)?  Otherwise P3 is never needed.
+    int big = 0;
+    {
+        const float *x6 = reinterpret_cast<const float *>(sm + 3 * PLC);
+#pragma unroll 1
+        for (int c = tid; c < TL::PLB; c += THREADS) big |= x6[c * 4] < kSentTest;
+    }
+    const bool ns8 = __syncthreads_or(big) || (a.dbg_skip & 8);
+
     // ------------------------------------------------------------ the four sub-sweeps
     unsigned my_trials = 0, my_acc = 0;
-    const float hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
-    const int ox0 = H + exl, oy0 = H + eyl;         // region coordinates of the owned tile's corner
-    const int nox = min(TX, cps - (int)blockIdx.x * TX), noy = min(TY, g.rows - (int)blockIdx.y * TY);
-
+    if (!(a.dbg_skip & 1)) {
+        if (!ns8) {
 #pragma unroll 1
-    for (int k = 0; k < ((a.dbg_skip & 1) ? 0 : 4); k++) {
-        const int lo = k + 1;                       // cells closer than lo to the region edge are stale
-        const int pi = ((int)((a.offmask >> (2 * k)) & 1u) - rx0) & 1;       // region-column parity of the active colour
-        const int pj = ((int)((a.offmask >> (2 * k + 1)) & 1u) - (g.row0 + ry0)) & 1;
-        const int i = lo + ((pi - lo) & 1) + 2 * aq, j = lo + ((pj - lo) & 1) + 2 * bq;
-        if (i < RX - lo && j < RY - lo) {
-            const int is = i + xs, par = is & 1;
-            float4 *pown = sm + j * PITCH + par * HB + (is >> 1);
-            const float4 *pL = sm + j * PITCH + (1 - par) * HB + ((is - 1) >> 1);      // left neighbour; right = pL + 1
-            const float4 x03 = pown[0], x47 = pown[PLC], y03 = pown[2 * PLC], y47 = pown[3 * PLC];
-            const int cnt = decode_cnt(x47.w, y47.w);
-            if (cnt != 0) {                         // subsweep.h:252-254
-                const bool owned = (unsigned)(i - ox0) < (unsigned)nox && (unsigned)(j - oy0) < (unsigned)noy;
-                int gx = rx0 + i, gy = g.row0 + ry0 + j;
-                gx += gx < 0 ? cps : 0; gx -= gx >= cps ? cps : 0;
-                gy += gy < 0 ? cps : 0; gy -= gy >= cps ? cps : 0;
-                const uint32_t cell_id = (uint32_t)gy * (uint32_t)cps + (uint32_t)gx;
-
-                // neighbour part of one trial: smallest d2 against the 3 neighbour cells that can
-                // hold a disk closer than sigma (w >= 2 sigma), or -1 when the proposal leaves the
-                // cell (out_of_bound subsweep.h:73-88)
-                auto neighbours_min_d2 = [&](const float px, const float py) -> float {
-                    const bool inb = px > 0.0f && px <= w && py > 0.0f && py <= w;
-                    const bool goL = px <= hw, goD = py <= hw;
-                    const float npxs = -__fadd_rn(px, goL ? w : -w);     // -(px - helper*w), subsweep.h:139-151
-                    const float npys = -__fadd_rn(py, goD ? w : -w);
-                    const float4 *pH = pL + (goL ? 0 : 1);
-                    const int dV = goD ? -PITCH : PITCH;
-                    float m = cell_min_d2<PLC>(pH, npxs, -py);
-                    m = fminf(m, cell_min_d2<PLC>(pown + dV, -px, npys));
-                    m = fminf(m, cell_min_d2<PLC>(pH + dV, npxs, npys));
-                    return inb ? m : -1.0f;      // out of the cell: rejected whatever the neighbours say
-                };
-
-                float ox[8] = { x03.x, x03.y, x03.z, x03.w, x47.x, x47.y, x47.z, x47.w };
-                float oy[8] = { y03.x, y03.y, y03.z, y03.w, y47.x, y47.y, y47.z, y47.w };
-                uint32_t rw[8];
-                philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.seed_lo, g.seed_hi, rw[0], rw[1], rw[2], rw[3]);
-                philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.seed_lo, g.seed_hi, rw[4], rw[5], rw[6], rw[7]);
-                // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const uint32_t b16 = ((rw[2 * s] & 0xFFu) << 8) | (rw[2 * s + 1] & 0xFFu);
-                    const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
-                    const int jj = s + (int)((b16 * (uint32_t)mrem) >> 16);
-                    const float tx = ox[s], ty = oy[s];
-                    float nx = tx, ny = ty;
-#pragma unroll
-                    for (int q = s + 1; q < 8; q++) {
-                        const bool p = (jj == q);
-                        nx = p ? ox[q] : nx; ny = p ? oy[q] : ny;
-                        ox[q] = p ? tx : ox[q]; oy[q] = p ? ty : oy[q];
-                    }
-                    ox[s] = nx; oy[s] = ny;
-                }
-                // trials 0..3 move slot s mod cnt (subsweep.h:279-297), all register indices static
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const bool cA = cnt > s;                            // slot == s
-                    const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
-                    const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
-                    const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-                    const float px = __fmaf_rn(signed_odd24(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
-                    const float py = __fmaf_rn(signed_odd24(rw[2 * s + 1]), dscale, y);
-                    my_trials += owned ? 1u : 0u;
-                    float m = neighbours_min_d2(px, py);
-                    // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
-                    const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
-                    float2 d01 = pair2(ox[0], ox[1], oy[0], oy[1], npx, npy);
-                    float2 d23 = pair2(ox[2], ox[3], oy[2], oy[3], npx, npy);
-                    const float2 d45 = pair2(ox[4], ox[5], oy[4], oy[5], npx, npy);
-                    const float2 d67 = pair2(ox[6], ox[7], oy[6], oy[7], npx, npy);
-                    const float big = 3.0e38f;
-                    if (s == 0) d01.x = big;
-                    if (s == 1) { d01.y = cA ? big : d01.y; d01.x = cA ? d01.x : big; }
-                    if (s == 2) { d23.x = cA ? big : d23.x; d01.x = cA ? d01.x : big; }
-                    if (s == 3) { d23.y = cA ? big : d23.y; d01.y = cB ? big : d01.y; d01.x = (cA | cB) ? d01.x : big; }
-                    m = fminf(m, fminf(fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)),
-                                       fminf(fminf(d45.x, d45.y), fminf(d67.x, d67.y))));
-                    // accept_move subsweep.h:194-217 (hard disks: accept iff in bounds and no overlap)
-                    const bool acc = !(m < sigma2);
-                    my_acc += (acc && owned) ? 1u : 0u;
-                    if (s == 0) { ox[0] = acc ? px : ox[0]; oy[0] = acc ? py : oy[0]; }
-                    else {
-                        const bool w0 = acc & !cA & !cB, w1 = acc & cB, ws = acc & cA;
-                        ox[s] = ws ? px : ox[s]; oy[s] = ws ? py : oy[s];
-                        ox[0] = w0 ? px : ox[0]; oy[0] = w0 ? py : oy[0];
-                        if (s == 3) { ox[1] = w1 ? px : ox[1]; oy[1] = w1 ? py : oy[1]; }
-                    }
-                }
-                // cpy_D_sh_to_Disk subsweep.h:29-36 (shuffled order is written back, like the reference)
-                pown[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
-                pown[PLC] = make_float4(ox[4], ox[5], ox[6], ox[7]);
-                pown[2 * PLC] = make_float4(oy[0], oy[1], oy[2], oy[3]);
-                pown[3 * PLC] = make_float4(oy[4], oy[5], oy[6], oy[7]);
+            for (int k = 0; k < 4; k++) {
+                colour_pass<6, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                __syncthreads();
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                colour_pass<8, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                __syncthreads();
             }
         }
-        __syncthreads();
     }
 
-    // ------------------------------------------------------------ shiftCells(f, d) of this sweep, owned cells, in place
+    // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
     if (do_shift) {
-        const float d = a.shift_d;
-        const float sshift = __fmul_rn(w, (float)sdir);                 // shiftCells.h:84-86
-        // One thread owns a strip of K consecutive owned cells along the shift axis and walks it
-        // from the downstream end to the upstream end: cell u is rewritten only after raw cell
-        // u+1 has been read.  The raw cell after the strip (next strip, or the extra upstream
-        // row / column) is read before the barrier.
-        constexpr int SEG1 = THREADS / TX, K1 = (TY + SEG1 - 1) / SEG1;     // f = 1: column strips of K1 rows
-        constexpr int SEG0 = THREADS / TY < 8 ? THREADS / TY : 8, K0 = (TX + SEG0 - 1) / SEG0;   // f = 0: row strips of K0 columns
-        int i0, j0, len, di, dj;
-        if (a.shift_f == 1) {
-            const int seg = tid / TX, col = tid - seg * TX, k0 = seg * K1;
-            len = (seg < SEG1 && k0 < TY) ? min(K1, TY - k0) : 0;
-            i0 = ox0 + col; j0 = oy0 + (sdir > 0 ? k0 : TY - 1 - k0);
-            di = 0; dj = sdir;
-        } else {
-            const int row = tid / SEG0, seg = tid - row * SEG0, k0 = seg * K0;
-            len = (row < TY && k0 < TX) ? min(K0, TX - k0) : 0;
-            j0 = oy0 + row; i0 = ox0 + (sdir > 0 ? k0 : TX - 1 - k0);
-            di = sdir; dj = 0;
-        }
-        auto cell_ptr = [&](int i, int j) -> float4 * {
-            const int is = i + xs;
-            return sm + j * PITCH + (is & 1) * HB + (is >> 1);
-        };
-        auto load_cell = [&](int i, int j, CellRegs &c) {
-            const float4 *p = cell_ptr(i, j);
-            c.x03 = p[0]; c.x47 = p[PLC]; c.y03 = p[2 * PLC]; c.y47 = p[3 * PLC];
-            c.cnt = decode_cnt(c.x47.w, c.y47.w);
-        };
-        CellRegs cur, edge;
-        if (len > 0) {
-            load_cell(i0, j0, cur);
-            load_cell(i0 + len * di, j0 + len * dj, edge);
-        }
-        __syncthreads();
-        constexpr int KMAX = K0 > K1 ? K0 : K1;
-#pragma unroll
-        for (int u = 0; u < KMAX; u++) {
-            if (u < len) {
-                const int i = i0 + u * di, j = j0 + u * dj;
-                CellRegs up = edge;
-                if (u + 1 < len) load_cell(i + di, j + dj, up);
-                float4 *p = cell_ptr(i, j);
-                p[0] = make_float4(kSent, kSent, kSent, kSent);
-                p[PLC] = make_float4(kSent, kSent, kSent, kSent);
-                p[2 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
-                p[3 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
-                float *fx = reinterpret_cast<float *>(p);
-                int dropped, nNew;
-                if (a.shift_f == 0) nNew = shift_into_tile<0, PLC>(cur, up, d, w, sshift, fx, &dropped);
-                else nNew = shift_into_tile<1, PLC>(cur, up, d, w, sshift, fx, &dropped);
-                if (nNew < PMC_NMAX) fx[3 * PLC * 4 + 3] = __int_as_float(nNew);
-                if (dropped) {
-                    atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
-                    if ((unsigned)(i - ox0) < (unsigned)nox && (unsigned)(j - oy0) < (unsigned)noy)
-                        atomicAdd(&ctr->lost, (unsigned long long)dropped);
-                }
-                cur = up;
-            }
-        }
-        __syncthreads();
+        if (!ns8) shift_pass<6, TX, TY>(sm, t, a, g.w, sdir, tid, ctr);
+        else shift_pass<8, TX, TY>(sm, t, a, g.w, sdir, tid, ctr);
     }
 
     // ------------------------------------------------------------ owned tile -> HBM (+ periodic images into the margins)
     if (!(a.dbg_skip & 4)) {
         // thread -> fixed (chunk column h, parity, plane), rows strided: a warp stores runs of
-        // TX/2 consecutive float4
+        // TX/2 consecutive float4.  After the shift the staged cells are in plain plane order
+        // (x0-3 | x4-7 | y0-3 | y4-7) and are converted to P0..P3 here.
         constexpr int HX = TX / 2, RSTEP = THREADS / (8 * HX);
         static_assert(THREADS % (8 * HX) == 0, "store mapping");
         const int h = tid % HX, pr = (tid / HX) & 1, pl = (tid / (2 * HX)) & 3, rg = tid / (8 * HX);
         const int ox = 2 * h + pr;                                  // owned column (parity == internal column parity)
         const int ux = blockIdx.x * TX + ox, uy0 = blockIdx.y * TY;
-        if (ox < nox) {
-            const int is = ox0 + ox + xs;
-            const float4 *src = sm + pl * PLC + (is & 1) * HB + (is >> 1) + (oy0 + rg) * PITCH;
+        if (ox < t.nox) {
+            const int is = t.ox0 + ox + t.xs;
+            const float4 *cell0 = sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH;
+            // source of output plane pl: P0 <- x03, P1 <- y03, P2 <- x47.xy y47.xy, P3 <- x47.zw y47.zw
+            const float4 *src = cell0 + (do_shift ? (pl == 0 ? 0 : (pl == 1 ? 2 : 1)) : pl) * PLC;
+            const int half = (pl == 3) ? 2 : 0;                     // float offset of the pair inside x47 / y47
+            const bool split = do_shift && pl >= 2;
+            auto fetch = [&](const float4 *s) -> float4 {
+                if (!split) return *s;
+                const float2 xa = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(s) + half);
+                const float2 ya = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(s + 2 * PLC) + half);
+                return make_float4(xa.x, xa.y, ya.x, ya.y);
+            };
             const long long rstride = (long long)8 * g.CH;          // float4 chunks per internal row
             float4 *dst = dout + ((long long)(kMY + uy0 + rg) * 4 + pl) * 2 * g.CH + (long long)pr * g.CH + ((kMX + ux) >> 1);
             // periodic image of this column inside the margins (cps is even: parity is kept)
             const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);
-            const bool yedge = g.wrap_y && (uy0 < kMY || uy0 + noy > g.rows - kMY);
+            const bool yedge = g.wrap_y && (uy0 < kMY || uy0 + t.noy > g.rows - kMY);
             if (!ximg && !yedge) {
 #pragma unroll 2
-                for (int oyy = rg; oyy < noy; oyy += RSTEP) {
-                    *dst = *src;
+                for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
+                    *dst = fetch(src);
                     src += RSTEP * PITCH; dst += RSTEP * rstride;
                 }
             } else {
 #pragma unroll 1
-                for (int oyy = rg; oyy < noy; oyy += RSTEP) {
-                    const float4 v = *src;
+                for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
+                    const float4 v = fetch(src);
                     const int uy = uy0 + oyy;
                     dst[0] = v;
                     if (ximg) dst[ximg] = v;
@@ -406,10 +492,9 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
 }
 
 // ------------------------------------------------------------------ caller layout <-> internal layout
-// caller: disk float[cell][2][8] (= 4 float4 per cell: x03, x47, y03, y47) + int16 n[cell]
-// (include/pmc.h).  One thread per (internal cell, plane); margins are filled with the
-// periodic images, everything beyond with empty cells.
-__global__ void import4_kernel(const float4 *__restrict__ disk, const int16_t *__restrict__ n,
+// caller: disk float[cell][2][8] + int16 n[cell] (include/pmc.h).  One thread per (internal
+// cell, plane); margins are filled with the periodic images, everything beyond with empty cells.
+__global__ void import4_kernel(const float *__restrict__ disk, const int16_t *__restrict__ n,
                                float4 *__restrict__ out, Geom4 g, int ghost)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -429,44 +514,64 @@ __global__ void import4_kernel(const float4 *__restrict__ disk, const int16_t *_
         src = (long long)(ly + ghost) * g.cps + gx;     // the caller's array carries `ghost` rows on each side
         have = have && (ly + ghost >= 0) && (ly + ghost < g.rows + 2 * ghost);
     }
-    float4 v = pl < 2 ? make_float4(kSent, kSent, kSent, kSent) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // first slot of this plane's x pair / quad, number of slots per coordinate
+    const int s0 = pl < 2 ? 0 : (pl == 2 ? 4 : 6), ns = pl < 2 ? 4 : 2;
+    float v[4];
+    if (pl == 0) { v[0] = v[1] = v[2] = v[3] = kSent; }
+    else if (pl == 1) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+    else { v[0] = v[1] = kSent; v[2] = v[3] = 0.f; }
     if (have) {
         int cnt = (int)__ldg(n + src);
         cnt = cnt < 0 ? 0 : (cnt > PMC_NMAX ? PMC_NMAX : cnt);
-        const float4 q = __ldg(disk + src * 4 + pl);
-        const int s0 = (pl & 1) * 4;
-        const float fill = pl < 2 ? kSent : 0.0f;       // the caller's unused slots may hold garbage
-        v.x = s0 + 0 < cnt ? q.x : fill; v.y = s0 + 1 < cnt ? q.y : fill;
-        v.z = s0 + 2 < cnt ? q.z : fill; v.w = s0 + 3 < cnt ? q.w : fill;
-        if (pl == 3 && cnt < PMC_NMAX) v.w = __int_as_float(cnt);
+        const float *c = disk + src * 16;               // x0..x7, y0..y7
+        if (pl == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (q < cnt) v[q] = __ldg(c + q);
+        } else if (pl == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (q < cnt) v[q] = __ldg(c + 8 + q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                if (q < ns && s0 + q < cnt) { v[q] = __ldg(c + s0 + q); v[2 + q] = __ldg(c + 8 + s0 + q); }
+            // in-band count (the caller's unused slots may hold garbage: never copied)
+            if (pl == 2 && cnt < 6) v[3] = __int_as_float(cnt);
+            if (pl == 3 && cnt < PMC_NMAX) v[3] = __int_as_float(cnt);
+        }
     }
-    out[((long long)(Y * 4 + pl) * 2 + (X & 1)) * g.CH + (X >> 1)] = v;
+    out[((long long)(Y * 4 + pl) * 2 + (X & 1)) * g.CH + (X >> 1)] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// internal -> caller layout: every cell of the caller's array (slab: ghost rows included)
+// internal -> caller layout: every cell of the caller's array (slab: ghost rows included);
+// one thread per (cell, caller chunk): x03, x47, y03, y47
 __global__ void export4_kernel(const float4 *__restrict__ in, float4 *__restrict__ disk,
                                int16_t *__restrict__ n, Geom4 g, int ghost)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long cell = t >> 2;
-    const int pl = (int)(t & 3);
-    const long long ncell = (long long)(g.rows + 2 * ghost) * g.cps;
-    const bool live = cell < ncell;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        const int lr = (int)(cell / g.cps), gx = (int)(cell - (long long)lr * g.cps);
-        const int X = gx + kMX, Y = lr - ghost + kMY;
-        v = __ldg(in + ((long long)(Y * 4 + pl) * 2 + (X & 1)) * g.CH + (X >> 1));
+    const int ch = (int)(t & 3);
+    if (cell >= (long long)(g.rows + 2 * ghost) * g.cps) return;
+    const int lr = (int)(cell / g.cps), gx = (int)(cell - (long long)lr * g.cps);
+    const int X = gx + kMX, Y = lr - ghost + kMY;
+    const float4 *cp = in + ((long long)(Y * 4) * 2 + (X & 1)) * g.CH + (X >> 1);
+    const long long ps = (long long)2 * g.CH;           // plane stride
+    const float4 p3 = __ldg(cp + 3 * ps);
+    const int cnt = decode_cnt8(p3);
+    float4 v;
+    int s0;
+    if (ch == 0) { v = __ldg(cp); s0 = 0; }
+    else if (ch == 2) { v = __ldg(cp + ps); s0 = 0; }
+    else {
+        const float4 p2 = __ldg(cp + 2 * ps);
+        v = ch == 1 ? make_float4(p2.x, p2.y, p3.x, p3.y) : make_float4(p2.z, p2.w, p3.z, p3.w);
+        s0 = 4;
     }
-    // the four lanes of a cell are adjacent: lane 1 holds x[7], lane 3 holds y[7]
-    const int base = (threadIdx.x & 31) & ~3;
-    const float x7 = __shfl_sync(0xffffffffu, v.w, base + 1);
-    const float y7 = __shfl_sync(0xffffffffu, v.w, base + 3);
-    if (!live) return;
-    const int cnt = decode_cnt(x7, y7);
-    if (pl == 3 && cnt < PMC_NMAX) v.w = 0.0f;          // pmc.h: unused slots hold x = sentinel, y = 0
-    disk[cell * 4 + pl] = v;
-    if (pl == 0) n[cell] = (int16_t)cnt;
+    // pmc.h: unused slots hold x = sentinel, y = 0 (the in-band counts are internal)
+    const float fill = ch < 2 ? kSent : 0.f;
+    v.x = s0 + 0 < cnt ? v.x : fill; v.y = s0 + 1 < cnt ? v.y : fill;
+    v.z = s0 + 2 < cnt ? v.z : fill; v.w = s0 + 3 < cnt ? v.w : fill;
+    disk[cell * 4 + ch] = v;
+    if (ch == 0) n[cell] = (int16_t)cnt;
 }
 
 constexpr int kTX = 24, kTY = 40, kMinB = 2;
@@ -520,7 +625,7 @@ int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g)
 cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out, cudaStream_t st)
 {
     const long long threads = (long long)2 * g.CH * g.ROWS * 4;
-    import4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(disk, n, out, g, ghost);
+    import4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float *)disk, n, out, g, ghost);
     return cudaGetLastError();
 }
 

@@ -6,7 +6,7 @@ import numpy as np, torch
 import pmc_b200
 from oracle import oracle as O
 
-skip = int(os.environ.get("PMC_DBG_SKIP", "0"))
+skip = int(os.environ.get("PMC_DBG_SKIP", "0"))  # 8 = force the 8-slot instantiation
 N = int(os.environ.get("PMC_N", 2 ** 14))
 S = int(os.environ.get("PMC_S", 3))
 kw = dict(phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1, seed=1234)
