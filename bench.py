@@ -35,8 +35,9 @@ N_M, NMAX, SIGMA, CELL_W, SEED = 4, 8, 1.0, 2.0, 1234
 METRIC = "hard-disk trial moves/sec"
 UNIT = "moves/s"
 
-# ncu --set full capture of sweep_tile_kernel<4,...> at N=2^24 (profiles/): dram bytes per launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_summary.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum per launch
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 311.1e6 + 257.7e6}
 
 
 def algorithmic_bytes_per_sweep(n_particles, n_cells):
@@ -229,6 +230,7 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     c = mc.counters()
+    kernel_ms, kernel_launches = mc.kernel_time()   # CUDA events around the fused sweep kernels alone
     trials = torch.tensor([c["trials"], c["accepted"], c["lost"], c["status"]], dtype=torch.float64, device="cuda")
     tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist:
@@ -237,7 +239,10 @@ def main():
     ms = float(tmax.item())
     tot_trials, tot_acc, tot_lost, status = (float(x) for x in trials.tolist())
     value = tot_trials / (ms * 1e-3)
-    launches_per_step = S + 1          # S fused sweep kernels + 1 stand-alone shiftCells per pmc_sweep call
+    # per pmc_sweep call: layout import + S fused sweep kernels + layout export (fast path), or
+    # S fused kernels + 1 stand-alone shiftCells (generic path)
+    fast = kernel_launches > 0
+    launches_per_step = S + 2 if fast else S + 1
     n_sweeps_timed = args.steps * S
 
     # invariants after the timed region (cheap, device side)
@@ -253,12 +258,17 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    ms_per_launch = ms / n_sweeps_timed          # upper bound: includes 1 stand-alone shift per step
+    if fast:
+        ms_per_launch = kernel_ms / kernel_launches     # events bracket the S sweep kernels of each call
+        kname = "sweep4_kernel<24,40,2> (one launch = one MC sweep: 4 colours + shiftCells)"
+    else:
+        ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
+        kname = "sweep_tile_kernel<4,26,32,320,2,*> (generic path)"
     alg_bytes = algorithmic_bytes_per_sweep(N, g.n_cells) / n_ranks      # per launch per GPU
     achieved = alg_bytes / (ms_per_launch * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "sweep_tile_kernel<4,32,384,2>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(workload) if n_ranks == 1 else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_move": alg_bytes * n_ranks / (tot_trials / n_sweeps_timed),
                 "ms_per_launch": ms_per_launch,

@@ -107,6 +107,7 @@ def lib():
     L.pmc_get_counters.argtypes = [hp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     L.pmc_reset_counters.argtypes = [hp]
+    L.pmc_get_kernel_time.argtypes = [hp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.pmc_check.argtypes = [hp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     L.pmc_gr_hist.argtypes = [hp, vp, vp, C.c_float, C.c_int, vp]
     L.pmc_pressure_from_hist.argtypes = [hp, vp, C.c_float, C.c_int, C.c_int64, vp,
@@ -124,7 +125,7 @@ EXPORTS = ["pmc_create", "pmc_destroy", "pmc_get_geometry", "pmc_r_bytes", "pmc_
            "pmc_n_bytes", "pmc_set_stream", "pmc_set_blocking", "pmc_synchronize",
            "pmc_error_string", "pmc_init_r", "pmc_assign", "pmc_subsweep", "pmc_shift_cells",
            "pmc_schedule", "pmc_colour_to_off", "pmc_sweep", "pmc_get_counters",
-           "pmc_reset_counters", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
+           "pmc_reset_counters", "pmc_get_kernel_time", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
            "pmc_disk_to_r_host", "pmc_run_host", "pmc_comm_unique_id", "pmc_comm_init",
            "pmc_exchange_ghosts"]
 
@@ -227,6 +228,12 @@ class ParallelMC:
 
     def reset_counters(self):
         _ck(lib().pmc_reset_counters(self._h))
+
+    def kernel_time(self):
+        """(ms, launches) of the fused sweep kernels since the last reset_counters()."""
+        ms, nl = C.c_double(), C.c_longlong()
+        _ck(lib().pmc_get_kernel_time(self._h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
 
     def check(self, disk, n):
         out = (C.c_int64 * 4)()

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
 #include <vector>
 
 #ifndef M_PI
@@ -84,6 +85,10 @@ struct pmc_handle {
     int v4_padded;              // both buffers hold valid cells everywhere (padding included)
     Geom4 g4;
     float4 *v4_buf[2];
+    // device time of the fused sweep kernels alone (bench.py roofline): one event pair per pmc_sweep call
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *ktime_pending;
+    double ktime_ms;
+    long long ktime_launches, ktime_pending_launches;
     alignas(64) unsigned char v4_tmap[2][128];
 };
 
@@ -213,6 +218,10 @@ int pmc_destroy(pmc_handle *h)
     cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
     cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
     cudaFree(h->v4_buf[0]); cudaFree(h->v4_buf[1]);
+    if (h->ktime_pending) {
+        for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        delete h->ktime_pending;
+    }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     free(h);
     return 0;
@@ -355,6 +364,7 @@ int pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
     return finish(h);
 }
 
+extern "C" int pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launches);
 static size_t v4_bytes(const pmc_handle *h) { return (size_t)2 * h->g4.CH * h->g4.ROWS * 4 * sizeof(float4); }
 
 // slab ring on the internal layout: whole rows (4 planes x 2 parities x CH chunks) are contiguous
@@ -395,6 +405,10 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     }
     int cur = 0;
     static const int dbg = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
+    cudaEvent_t k0, k1;
+    CK(cudaEventCreate(&k0));
+    CK(cudaEventCreate(&k1));
+    CK(cudaEventRecord(k0, h->stream));
     for (int t = 0; t < n_sweeps; t++) {
         const uint64_t sweep = sweep0 + (uint64_t)t;
         int order[4], f;
@@ -416,6 +430,11 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         if (rc) return rc;
         cur ^= 1;
     }
+    CK(cudaEventRecord(k1, h->stream));
+    if (!h->ktime_pending) h->ktime_pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
+    h->ktime_pending->push_back(std::make_pair(k0, k1));
+    h->ktime_pending_launches += n_sweeps;
+    if (h->ktime_pending->size() > 4096) { double ms; long long nl; pmc_get_kernel_time(h, &ms, &nl); }
     CK(pmc4_launch_export(h->g4, ghost, h->v4_buf[cur], (float4 *)d_disk, d_n, h->stream));
     return finish(h);
 }
@@ -482,9 +501,31 @@ int pmc_get_counters(pmc_handle *h, uint64_t *trials, uint64_t *accepted, uint64
     return 0;
 }
 
+// device time spent in the fused sweep kernels (pmc_sweep fast path) since the last reset, and
+// how many of them were launched: the per-launch time bench.py quotes against the roofline
+int pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launches)
+{
+    if (!h) return PMC_E_INVALID;
+    if (h->ktime_pending && !h->ktime_pending->empty()) {
+        CK(cudaStreamSynchronize(h->stream));
+        for (auto &pr : *h->ktime_pending) {
+            float e = 0.0f;
+            if (cudaEventElapsedTime(&e, pr.first, pr.second) == cudaSuccess) h->ktime_ms += e;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        h->ktime_pending->clear();
+        h->ktime_launches += h->ktime_pending_launches;
+        h->ktime_pending_launches = 0;
+    }
+    if (ms) *ms = h->ktime_ms;
+    if (launches) *launches = h->ktime_launches;
+    return 0;
+}
+
 int pmc_reset_counters(pmc_handle *h)
 {
     if (!h) return PMC_E_INVALID;
+    { double ms; long long nl; pmc_get_kernel_time(h, &ms, &nl); h->ktime_ms = 0.0; h->ktime_launches = 0; }
     CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
     return finish(h);
 }

@@ -75,6 +75,17 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
+// forced 16-byte shared-memory load (ptxas otherwise splits a float4 whose components are
+// consumed one by one into four LDS.32, each a 4-way bank conflict at a 16-byte lane stride)
+template <int BYTE_OFF>
+__device__ __forceinline__ float4 lds128(unsigned saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr), "n"(BYTE_OFF));
+    return v;
+}
+
 // in-band count: y7 when fewer than 8 disks (P3 = x6 x7 y6 y7), y5 when fewer than 6 (P2 = x4 x5 y4 y5)
 __device__ __forceinline__ int decode_cnt8(const float4 &p3) { return p3.y < kSentTest ? 8 : __float_as_int(p3.w); }
 __device__ __forceinline__ int decode_cnt6(const float4 &p2) { return p2.y < kSentTest ? 6 : __float_as_int(p2.w); }
@@ -182,9 +193,10 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     const int is = i + t.xs, par = is & 1;
     float4 *pown = sm + j * PITCH + par * HB + (is >> 1);
     const float4 *pL = sm + j * PITCH + (1 - par) * HB + ((is - 1) >> 1);      // left neighbour; right = pL + 1
-    const float4 p0 = pown[0], p1 = pown[PLC], p2 = pown[2 * PLC];
+    const unsigned sown = smem_u32(pown);
+    const float4 p0 = lds128<0>(sown), p1 = lds128<PLC * 16>(sown), p2 = lds128<2 * PLC * 16>(sown);
     float4 p3 = make_float4(kSent, kSent, 0.f, 0.f);
-    if (NS == 8) p3 = pown[3 * PLC];
+    if (NS == 8) p3 = lds128<3 * PLC * 16>(sown);
     const int cnt = NS == 8 ? decode_cnt8(p3) : decode_cnt6(p2);
     if (cnt == 0) return;                       // subsweep.h:252-254
     const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
