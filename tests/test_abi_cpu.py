@@ -58,3 +58,31 @@ def test_host_schedule_matches_oracle_without_gpu(built):
     from oracle import oracle as O
     for c in range(4):
         assert pmc_b200.ParallelMC.colour_to_off(c) == O.Oracle.colour_to_off(c)
+
+
+def _build_start_driver():
+    """the reference's main() (start.cu:169-272) as plain C on top of the C-ABI."""
+    import subprocess
+    import pmc_b200
+    exe = os.path.join(ROOT, "examples", "start_driver")
+    src = os.path.join(ROOT, "examples", "start_driver.c")
+    libdir = os.path.dirname(pmc_b200.LIB_PATH)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + cuda + "/include",
+                           src, "-L" + libdir, "-lpmc_b200", "-L" + cuda + "/lib64", "-lcudart",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda + "/lib64", "-o", exe])
+    return exe
+
+
+def test_c_driver_of_integration_md_compiles_and_links(built):
+    exe = _build_start_driver()
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_c_driver_runs_the_reference_protocol(built):
+    import subprocess
+    exe = _build_start_driver()
+    out = subprocess.run([exe, "16384", "6"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "fused_equals_per_call=1" in out.stdout
