@@ -151,7 +151,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--sweeps-per-step", type=int, default=100)
+    ap.add_argument("--sweeps-per-step", type=int, default=1000,
+                    help="MC sweeps per step; default = the reference's MCpasses (start.cu:24)")
     ap.add_argument("--burn-in", type=int, default=300)
     ap.add_argument("--ref-sweeps", type=int, default=2, help="sweeps per step of the CPU arm")
     ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the cpu_baseline sample")

@@ -196,6 +196,13 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
     if (p.device >= 0) { cudaError_t e = cudaSetDevice(p.device); if (e != cudaSuccess) { free(h); return (int)e; } }
     cudaError_t e = cudaGetDevice(&h->device);
     if (e != cudaSuccess) { free(h); return (int)e; }
+    {   // stream-ordered scratch (cell-list build) stays cached in the device's default pool
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { free(h); return (int)e; }
     h->own_stream = true;
@@ -405,6 +412,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     }
     int cur = 0;
     static const int dbg = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
+    static const int pf_ahead = [] { const char *e = getenv("PMC_PREFETCH"); return e ? atoi(e) : 296; }();
     cudaEvent_t k0, k1;
     CK(cudaEventCreate(&k0));
     CK(cudaEventCreate(&k1));
@@ -425,6 +433,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
         a.shift_on = 1; a.shift_f = f; a.shift_d = d;
         a.dbg_skip = dbg;
+        a.prefetch_ahead = pf_ahead;
         CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream));
         int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1]);
         if (rc) return rc;

@@ -45,6 +45,7 @@ struct SweepArgs {
     int shift_on;           // apply a pending shiftCells(f, d) while staging the tile
     int shift_f;
     float shift_d;
+    int prefetch_ahead;     // fused fast path: L2-prefetch the tile of block id + this (0 = off)
     int dbg_skip;           // profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store
 };
 

@@ -75,6 +75,13 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
+// the same box, HBM -> L2 only: issued for the tile that a CTA slot of this wave will stage next
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tm, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // forced 16-byte shared-memory load (ptxas otherwise splits a float4 whose components are
 // consumed one by one into four LDS.32, each a 4-way bank conflict at a 16-byte lane stride)
 template <int BYTE_OFF>
@@ -400,6 +407,16 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         mbar_expect_tx(mbar, (unsigned)(4 * TL::PLB * 16));
 #pragma unroll
         for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, &tmap, 4 * ((X0 - t.xs) >> 1), 0, p, Y0, mbar);
+        if (a.prefetch_ahead > 0) {
+            // warm L2 for the tile a CTA slot freed by this wave will stage (blocks are issued in order)
+            const int nb = blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
+            if (nb < (int)(gridDim.x * gridDim.y)) {
+                const int by2 = nb / gridDim.x, bx2 = nb - by2 * gridDim.x;
+                const int X2 = bx2 * TX - H - exl + kMX, Y2 = by2 * TY - H - eyl + kMY;
+#pragma unroll
+                for (int p = 0; p < 4; p++) tma_prefetch_4d(&tmap, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
+            }
+        }
         mbar_wait(mbar, 0);     // one poller; the others observe the completed phase once
     }
     __syncthreads();
@@ -444,12 +461,11 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         // thread -> fixed (chunk column h, parity, plane), rows strided: a warp stores runs of
         // TX/2 consecutive float4.  After the shift the staged cells are in plain plane order
         // (x0-3 | x4-7 | y0-3 | y4-7) and are converted to P0..P3 here.
-        constexpr int HX = TX / 2, RSTEP = THREADS / (8 * HX);
-        static_assert(THREADS % (8 * HX) == 0, "store mapping");
+        constexpr int HX = TX / 2, RSTEP = THREADS / (8 * HX);   // threads beyond RSTEP * 8 * HX do not store
         const int h = tid % HX, pr = (tid / HX) & 1, pl = (tid / (2 * HX)) & 3, rg = tid / (8 * HX);
         const int ox = 2 * h + pr;                                  // owned column (parity == internal column parity)
         const int ux = blockIdx.x * TX + ox, uy0 = blockIdx.y * TY;
-        if (ox < t.nox) {
+        if (ox < t.nox && rg < RSTEP) {
             const int is = t.ox0 + ox + t.xs;
             const float4 *cell0 = sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH;
             // source of output plane pl: P0 <- x03, P1 <- y03, P2 <- x47.xy y47.xy, P3 <- x47.zw y47.zw
@@ -586,36 +602,65 @@ __global__ void export4_kernel(const float4 *__restrict__ in, float4 *__restrict
     if (ch == 0) n[cell] = (int16_t)cnt;
 }
 
-constexpr int kTX = 24, kTY = 40, kMinB = 2;
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
+// tile configurations (PMC_TILE4 selects; 0 is the tuned default)
+struct TileCfg { int tx, ty, hb, syb, h; };
+template <int TX, int TY> constexpr TileCfg cfg_of() { return { TX, TY, Tile4<TX, TY>::HB, Tile4<TX, TY>::SYB, Tile4<TX, TY>::H }; }
+constexpr TileCfg kCfgs[] = { cfg_of<24, 40>(), cfg_of<24, 24>(), cfg_of<24, 32>(), cfg_of<24, 48>() };
+
+int tile_index()
+{
+    static const int idx = [] {
+        const char *e = getenv("PMC_TILE4");
+        const int i = e ? atoi(e) : 0;
+        return (i >= 0 && i < (int)(sizeof(kCfgs) / sizeof(kCfgs[0]))) ? i : 0;
+    }();
+    return idx;
+}
+
+template <int TX, int TY, int MINB>
+cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a, Counters *ctr, cudaStream_t st)
+{
+    using TL = Tile4<TX, TY>;
+    auto kern = sweep4_kernel<TX, TY, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((g.cps + TX - 1) / TX, (g.rows + TY - 1) / TY);
+    kern<<<grid, TL::THREADS, TL::SMEM, st>>>(*(const CUtensorMap *)tmap_in, dout, g, a, ctr);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
-int pmc4_tile_x() { return kTX; }
-int pmc4_tile_y() { return kTY; }
+int pmc4_tile_x() { return kCfgs[tile_index()].tx; }
+int pmc4_tile_y() { return kCfgs[tile_index()].ty; }
 
 // rows / chunk columns the internal array needs so that every staged box is in bounds
 void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS)
 {
-    using TL = Tile4<kTX, kTY>;
-    const int gx = (cps + kTX - 1) / kTX, gy = (rows + kTY - 1) / kTY;
+    const TileCfg c = kCfgs[tile_index()];
+    const int gx = (cps + c.tx - 1) / c.tx, gy = (rows + c.ty - 1) / c.ty;
     // last staged column: kMX + (gx-1)*TX - H - 1 (rounded down to even) + 2*HB - 1
-    const int cols = kMX + (gx - 1) * kTX - TL::H + 2 * TL::HB + 2;
+    const int cols = kMX + (gx - 1) * c.tx - c.h + 2 * c.hb + 2;
     const int cols_img = cps + 2 * kMX;
-    const int c = cols > cols_img ? cols : cols_img;
-    *CH = (c + 1) / 2;
-    const int r = kMY + (gy - 1) * kTY - TL::H + TL::SYB + 1;
+    const int cc = cols > cols_img ? cols : cols_img;
+    *CH = (cc + 1) / 2;
+    const int r = kMY + (gy - 1) * c.ty - c.h + c.syb + 1;
     const int r_img = rows + 2 * kMY;
     *ROWS = r > r_img ? r : r_img;
 }
 
 int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g)
 {
-    using TL = Tile4<kTX, kTY>;
+    const TileCfg c = kCfgs[tile_index()];
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -626,7 +671,7 @@ int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g)
     }
     const cuuint64_t dims[4] = { (cuuint64_t)4 * g.CH, 2, 4, (cuuint64_t)g.ROWS };
     const cuuint64_t strides[3] = { (cuuint64_t)g.CH * 16, (cuuint64_t)g.CH * 32, (cuuint64_t)g.CH * 128 };
-    const cuuint32_t box[4] = { 4 * TL::HB, 2, 1, TL::SYB };
+    const cuuint32_t box[4] = { (cuuint32_t)(4 * c.hb), 2, 1, (cuuint32_t)c.syb };
     const cuuint32_t estr[4] = { 1, 1, 1, 1 };
     CUresult r = encode((CUtensorMap *)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -651,15 +696,10 @@ cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, floa
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
                               Counters *ctr, cudaStream_t st)
 {
-    using TL = Tile4<kTX, kTY>;
-    auto kern = sweep4_kernel<kTX, kTY, kMinB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    switch (tile_index()) {
+    case 1: return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st);
+    case 2: return launch_cfg<24, 32, 2>(g, tmap_in, dout, a, ctr, st);
+    case 3: return launch_cfg<24, 48, 1>(g, tmap_in, dout, a, ctr, st);
+    default: return launch_cfg<24, 40, 2>(g, tmap_in, dout, a, ctr, st);
     }
-    dim3 grid((g.cps + kTX - 1) / kTX, (g.rows + kTY - 1) / kTY);
-    kern<<<grid, TL::THREADS, TL::SMEM, st>>>(*(const CUtensorMap *)tmap_in, dout, g, a, ctr);
-    return cudaGetLastError();
 }
