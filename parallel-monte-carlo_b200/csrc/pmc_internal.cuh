@@ -75,6 +75,7 @@ struct Geom4 {
     int ROWS;                   // allocated rows
     float w, hw, sigma2, dscale;
     unsigned seed_lo, seed_hi;
+    unsigned pk0[10], pk1[10];  // Philox round keys seed + r * (0x9E3779B9, 0xBB67AE85): constant-bank operands
 };
 int pmc4_tile_x();
 int pmc4_tile_y();
@@ -100,6 +101,22 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// the same with the ten round keys precomputed on the host (kernel-parameter constants)
+__device__ __forceinline__ void philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                   const unsigned (&k0)[10], const unsigned (&k1)[10],
+                                                   uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0[r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1[r];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }

@@ -42,10 +42,12 @@ struct Tile4 {
     static constexpr int SYB = TY + 2 * H + 1;                   // staged rows
     static constexpr int PLB = PITCH * SYB;                      // chunks the TMA box brings per plane
     static constexpr int PLC = (PLB + 7) / 8 * 8;                // plane stride (128-byte aligned)
-    static constexpr int NAX = (TX + 2 * H) / 2, NAY = (TY + 2 * H) / 2;   // active cells per colour
+    // active cells per colour and row: at most 16 (half a warp, two conflict-free quarter-warps).
+    // TX = 24 always fits; TX = 26 fits when the tile carries no extra column (shift along y).
+    static constexpr int NAX = 16, NAY = (TY + 2 * H) / 2;
     static constexpr int THREADS = NAX * NAY;
     static constexpr size_t SMEM = (size_t)4 * PLC * 16 + 16;
-    static_assert(TX % 4 == 0 && TY % 2 == 0, "owned runs must be 32-byte aligned in HBM");
+    static_assert(TX % 2 == 0 && TY % 2 == 0 && TX + 2 * H <= 2 * NAX + 2, "tile shape");
     static_assert(4 * HB <= 256 && SYB <= 256, "TMA box extents");
 };
 
@@ -231,8 +233,8 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
     float oy[8] = { p1.x, p1.y, p1.z, p1.w, p2.z, p2.w, p3.z, p3.w };
     uint32_t rw[8];
-    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.seed_lo, g.seed_hi, rw[0], rw[1], rw[2], rw[3]);
-    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.seed_lo, g.seed_hi, rw[4], rw[5], rw[6], rw[7]);
+    philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.pk0, g.pk1, rw[0], rw[1], rw[2], rw[3]);
+    philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.pk0, g.pk1, rw[4], rw[5], rw[6], rw[7]);
     // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -611,6 +613,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 struct TileCfg { int tx, ty, hb, syb, h; };
 template <int TX, int TY> constexpr TileCfg cfg_of() { return { TX, TY, Tile4<TX, TY>::HB, Tile4<TX, TY>::SYB, Tile4<TX, TY>::H }; }
 constexpr TileCfg kCfgs[] = { cfg_of<24, 40>(), cfg_of<24, 24>(), cfg_of<24, 32>(), cfg_of<24, 48>() };
+// default (index 0): sweeps that shift along y use 26-column tiles (16, 15, 14, 13 active cells
+// per half-warp instead of 15, 14, 13, 12); the staged box is the same, so is the tensor map
+constexpr TileCfg kCfgWideY = cfg_of<26, 40>();
+static_assert(kCfgWideY.hb == kCfgs[0].hb && kCfgWideY.syb == kCfgs[0].syb, "one TMA box for both default tilings");
 
 int tile_index()
 {
@@ -649,7 +655,12 @@ void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS)
     const TileCfg c = kCfgs[tile_index()];
     const int gx = (cps + c.tx - 1) / c.tx, gy = (rows + c.ty - 1) / c.ty;
     // last staged column: kMX + (gx-1)*TX - H - 1 (rounded down to even) + 2*HB - 1
-    const int cols = kMX + (gx - 1) * c.tx - c.h + 2 * c.hb + 2;
+    int cols = kMX + (gx - 1) * c.tx - c.h + 2 * c.hb + 2;
+    if (tile_index() == 0) {
+        const int gxw = (cps + kCfgWideY.tx - 1) / kCfgWideY.tx;
+        const int colsw = kMX + (gxw - 1) * kCfgWideY.tx - kCfgWideY.h + 2 * kCfgWideY.hb + 2;
+        cols = colsw > cols ? colsw : cols;
+    }
     const int cols_img = cps + 2 * kMX;
     const int cc = cols > cols_img ? cols : cols_img;
     *CH = (cc + 1) / 2;
@@ -700,6 +711,8 @@ cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout,
     case 1: return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st);
     case 2: return launch_cfg<24, 32, 2>(g, tmap_in, dout, a, ctr, st);
     case 3: return launch_cfg<24, 48, 1>(g, tmap_in, dout, a, ctr, st);
-    default: return launch_cfg<24, 40, 2>(g, tmap_in, dout, a, ctr, st);
+    default:
+        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 40, 2>(g, tmap_in, dout, a, ctr, st);
+        return launch_cfg<26, 40, 2>(g, tmap_in, dout, a, ctr, st);
     }
 }
