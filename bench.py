@@ -199,7 +199,10 @@ def main():
     if n_ranks > 1:
         mc.comm_init_from_torch()
     g = mc.geom
-    r = mc.init_r()
+    # dense configurations: the reference's lattice (init_r) + burn-in; RSA jams at phi ~ 0.547
+    # (SURVEY H6), so random sequential addition serves the dilute configuration only
+    init = "rsa" if phi < 0.5 else "lattice"
+    r = mc.rsa(seed=SEED) if init == "rsa" else mc.init_r()
     disk, n = mc.assign(r)
     del r
     torch.cuda.empty_cache()
@@ -325,7 +328,7 @@ def main():
             "config": {"workload": workload, "n_particles": N, "phi": phi, "cells_per_side": g.cps,
                        "cell_w": g.w, "nmax": NMAX, "n_M": N_M, "move_delta": delta,
                        "proposal": "uniform square", "sweeps_per_step": S, "burn_in_sweeps": args.burn_in,
-                       "init": "square lattice (init_r) + burn-in", "seed": SEED,
+                       "init": ("random sequential addition (pmc_rsa_host)" if init == "rsa" else "square lattice (init_r)") + " + burn-in", "seed": SEED,
                        "l2": "state (%.0f MB per GPU) larger than L2, no flush" % (g.local_cells * 66 / 1e6),
                        "parallelism": "1 GPU" if n_ranks == 1 else f"{n_ranks} slabs of {g.rows} cell rows, NCCL ghost-row ring"},
             "acceptance": tot_acc / tot_trials, "trials": tot_trials, "lost": tot_lost, "status": int(status),

@@ -87,6 +87,8 @@ typedef struct pmc_handle pmc_handle;
 int  pmc_create(const pmc_params *params, pmc_handle **out);
 int  pmc_destroy(pmc_handle *h);
 int  pmc_get_geometry(const pmc_handle *h, pmc_geometry *g);
+/* the same derivation without a device or a handle (pure host maths) */
+int  pmc_geometry_from_params(const pmc_params *params, pmc_geometry *g);
 size_t pmc_r_bytes(const pmc_handle *h);      /* 2 * N * sizeof(float)            (rsize  start.cu:186) */
 size_t pmc_disk_bytes(const pmc_handle *h);   /* local_cells * 2 * nmax * 4       (disksize :188) */
 size_t pmc_n_bytes(const pmc_handle *h);      /* local_cells * sizeof(int16_t)    (nsize  :187) */
@@ -135,6 +137,19 @@ int  pmc_pressure_from_hist(const pmc_handle *h, const uint64_t *hist_host, floa
  * cell-then-slot order; returns the particle count in *n_found. */
 int  pmc_disk_to_r_host(pmc_handle *h, const float *d_disk, const int16_t *d_n,
                         float *r_host, int64_t *n_found);
+
+/* ---- initial configurations, trajectory, checkpoint
+ * Random sequential addition of n_particles disks (host code, no device needed; r_host is SoA
+ * [2][N] global coordinates like init_r's output).  RSA jams near phi = 0.547: PMC_E_UNSUPPORTED
+ * above that; dense configurations start from pmc_init_r (the reference's lattice). */
+int  pmc_rsa_host(const pmc_params *params, uint64_t seed, float *r_host, int64_t *attempts);
+/* one frame in the reference's dump format (create_dump kernel.cu:510-536, sample dumpR3.txt) */
+int  pmc_write_dump(pmc_handle *h, const float *d_disk, const int16_t *d_n, const char *path,
+                    int timestep, int append);
+/* binary checkpoint / restart of (params, sweep, counters, disk, n); new */
+int  pmc_save_checkpoint(pmc_handle *h, const float *d_disk, const int16_t *d_n, uint64_t sweep,
+                         const char *path);
+int  pmc_load_checkpoint(pmc_handle *h, const char *path, float *d_disk, int16_t *d_n, uint64_t *sweep);
 
 /* ---- end-to-end with HOST buffers: H2D(r) -> assign -> n_sweeps sweeps -> D2H(disk, n).
  * This is what a start.cu-equivalent driver does around its loop (start.cu:227-262). */

@@ -114,6 +114,11 @@ def lib():
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pmc_disk_to_r_host.argtypes = [hp, vp, vp, vp, C.POINTER(C.c_int64)]
     L.pmc_run_host.argtypes = [hp, vp, C.c_uint64, C.c_int, vp, vp]
+    L.pmc_geometry_from_params.argtypes = [C.POINTER(Params), C.POINTER(Geometry)]
+    L.pmc_rsa_host.argtypes = [C.POINTER(Params), C.c_uint64, vp, C.POINTER(C.c_int64)]
+    L.pmc_write_dump.argtypes = [hp, vp, vp, C.c_char_p, C.c_int, C.c_int]
+    L.pmc_save_checkpoint.argtypes = [hp, vp, vp, C.c_uint64, C.c_char_p]
+    L.pmc_load_checkpoint.argtypes = [hp, C.c_char_p, vp, vp, C.POINTER(C.c_uint64)]
     L.pmc_comm_unique_id.argtypes = [vp]
     L.pmc_comm_init.argtypes = [hp, vp]
     L.pmc_exchange_ghosts.argtypes = [hp, vp, vp]
@@ -126,8 +131,29 @@ EXPORTS = ["pmc_create", "pmc_destroy", "pmc_get_geometry", "pmc_r_bytes", "pmc_
            "pmc_error_string", "pmc_init_r", "pmc_assign", "pmc_subsweep", "pmc_shift_cells",
            "pmc_schedule", "pmc_colour_to_off", "pmc_sweep", "pmc_get_counters",
            "pmc_reset_counters", "pmc_get_kernel_time", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
-           "pmc_disk_to_r_host", "pmc_run_host", "pmc_comm_unique_id", "pmc_comm_init",
+           "pmc_disk_to_r_host", "pmc_run_host", "pmc_geometry_from_params", "pmc_rsa_host",
+           "pmc_write_dump", "pmc_save_checkpoint", "pmc_load_checkpoint", "pmc_comm_unique_id", "pmc_comm_init",
            "pmc_exchange_ghosts"]
+
+
+def geometry_from_params(n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1,
+                         seed=1234, cps_multiple=2, rank=0, n_ranks=1):
+    """Geometry derivation without a device (pure host maths in the C library)."""
+    p = Params(n_particles, phi, sigma_d, cell_w, nmax, n_M, move_delta, seed, cps_multiple, -1, rank, n_ranks)
+    g = Geometry()
+    _ck(lib().pmc_geometry_from_params(C.byref(p), C.byref(g)))
+    return g
+
+
+def rsa_host(n_particles, seed=1, **kw):
+    """Random sequential addition on the host (no device needed): numpy r [2][N], attempts."""
+    import numpy as np
+    p = Params(n_particles, kw.get("phi", 0.30), kw.get("sigma_d", 1.0), kw.get("cell_w", 2.0), 8, 4,
+               kw.get("move_delta", 0.1), 1234, kw.get("cps_multiple", 2), -1, 0, 1)
+    r = np.zeros((2, n_particles), dtype=np.float32)
+    att = C.c_int64()
+    _ck(lib().pmc_rsa_host(C.byref(p), seed, r.ctypes.data, C.byref(att)))
+    return r, att.value
 
 
 def _ck(rc):
@@ -270,6 +296,29 @@ class ParallelMC:
         """End to end with host buffers (torch CPU tensors, ideally pinned)."""
         _ck(lib().pmc_run_host(self._h, r_host.data_ptr(), sweep0, n_sweeps,
                                disk_host.data_ptr(), n_host.data_ptr()))
+
+    # initial configurations / trajectory / checkpoint ---------------------------
+    def rsa(self, seed=1):
+        """Random-sequential-addition configuration (host), uploaded as r [2][N]."""
+        import numpy as np
+        r = np.zeros((2, self.geom.n_particles), dtype=np.float32)
+        att = C.c_int64()
+        _ck(lib().pmc_rsa_host(C.byref(self.params), seed, r.ctypes.data, C.byref(att)))
+        self.rsa_attempts = att.value
+        return self.torch.from_numpy(r).to(self.device)
+
+    def write_dump(self, disk, n, path, timestep=0, append=False):
+        _ck(lib().pmc_write_dump(self._h, disk.data_ptr(), n.data_ptr(), path.encode(), timestep, int(append)))
+
+    def save_checkpoint(self, disk, n, sweep, path):
+        _ck(lib().pmc_save_checkpoint(self._h, disk.data_ptr(), n.data_ptr(), sweep, path.encode()))
+
+    def load_checkpoint(self, path, disk=None, n=None):
+        if disk is None:
+            disk, n = self.alloc_cells()
+        sw = C.c_uint64()
+        _ck(lib().pmc_load_checkpoint(self._h, path.encode(), disk.data_ptr(), n.data_ptr(), C.byref(sw)))
+        return disk, n, sw.value
 
     # multi-GPU ----------------------------------------------------------------
     def comm_init_from_torch(self):

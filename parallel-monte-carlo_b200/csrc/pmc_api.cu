@@ -112,26 +112,10 @@ static void host_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-extern "C" {
-
-const char *pmc_error_string(int code)
+// start.cu:14-27 as runtime values (identical arithmetic to oracle_make_geom); pure host maths
+static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g_out, pmc_geometry *pg_out)
 {
-    switch (code) {
-    case 0: return "success";
-    case PMC_E_INVALID: return "pmc: invalid argument";
-    case PMC_E_UNSUPPORTED: return "pmc: unsupported parameter (this build: nmax == 8)";
-    case PMC_E_OVERFLOW: return "pmc: a cell exceeded nmax particles";
-    case PMC_E_LOST: return "pmc: particles outside the box were dropped";
-    case PMC_E_NOT_SQUARE: return "pmc: init_r needs a perfect-square particle count";
-    case PMC_E_COMM: return "pmc: communicator error";
-    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pmc: unknown error";
-    }
-}
-
-int pmc_create(const pmc_params *pp, pmc_handle **out)
-{
-    if (!pp || !out) return PMC_E_INVALID;
-    pmc_params p = *pp;
+    pmc_params p = p_in;
     if (p.n_particles <= 0 || !(p.phi > 0.0f) || !(p.sigma_d > 0.0f) || !(p.cell_w >= p.sigma_d) ||
         p.n_M < 1 || p.n_M > 64 || !(p.move_delta > 0.0f)) return PMC_E_INVALID;
     if (p.nmax != PMC_NMAX) return PMC_E_UNSUPPORTED;
@@ -139,17 +123,12 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
     if (p.cps_multiple & 1) return PMC_E_INVALID;
     if (p.n_ranks < 1) p.n_ranks = 1;
     if (p.rank < 0 || p.rank >= p.n_ranks) return PMC_E_INVALID;
-
-    // start.cu:14-27 as runtime values; identical arithmetic to oracle_make_geom
     double L_d = sqrt((double)p.n_particles * M_PI * (double)p.sigma_d * (double)p.sigma_d / (4.0 * (double)p.phi));
     long long cps = (long long)floor(L_d / ((double)p.cps_multiple * (double)p.cell_w)) * p.cps_multiple;
     if (cps < 4 || cps > 46340) return PMC_E_INVALID;
     double w_d = L_d / (double)cps;
-
-    pmc_handle *h = (pmc_handle *)calloc(1, sizeof(pmc_handle));
-    if (!h) return PMC_E_INVALID;
-    h->p = p;
-    DevGeom &g = h->g;
+    DevGeom g;
+    memset(&g, 0, sizeof(g));
     g.cps = (int)cps;
     g.w = (float)w_d;
     g.L_box = (double)cps * (double)g.w;
@@ -166,21 +145,62 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
         g.row0 = 0; g.rows = g.cps; g.ghost = 0; g.wrap_y = 1;
     } else {
         // 1-D slabs of whole cell rows, even row count per slab so colours stay aligned
-        if (g.cps % (2 * p.n_ranks) != 0) { free(h); return PMC_E_INVALID; }
+        if (g.cps % (2 * p.n_ranks) != 0) return PMC_E_INVALID;
         g.rows = g.cps / p.n_ranks;
         g.row0 = p.rank * g.rows;
         g.ghost = kGhostRows;
         g.wrap_y = 0;
-        if (g.rows < 2 * kGhostRows) { free(h); return PMC_E_INVALID; }
+        if (g.rows < 2 * kGhostRows) return PMC_E_INVALID;
     }
     g.local_rows = g.rows + 2 * g.ghost;
-
-    pmc_geometry &pg = h->pg;
+    pmc_geometry pg;
+    memset(&pg, 0, sizeof(pg));
     pg.n_particles = p.n_particles; pg.cps = g.cps; pg.n_cells = cps * cps; pg.nmax = PMC_NMAX;
     pg.n_M = p.n_M; pg.w = g.w; pg.L = g.L; pg.sigma_d = p.sigma_d; pg.move_delta = p.move_delta;
     pg.row0 = g.row0; pg.rows = g.rows; pg.ghost_rows = g.ghost;
     pg.local_cells = (long long)g.local_rows * g.cps;
+    if (p_out) *p_out = p;
+    if (g_out) *g_out = g;
+    if (pg_out) *pg_out = pg;
+    return 0;
+}
 
+extern "C" {
+
+const char *pmc_error_string(int code)
+{
+    switch (code) {
+    case 0: return "success";
+    case PMC_E_INVALID: return "pmc: invalid argument";
+    case PMC_E_UNSUPPORTED: return "pmc: unsupported parameter (this build: nmax == 8; RSA: phi above the jamming density)";
+    case PMC_E_OVERFLOW: return "pmc: a cell exceeded nmax particles";
+    case PMC_E_LOST: return "pmc: particles outside the box were dropped";
+    case PMC_E_NOT_SQUARE: return "pmc: init_r needs a perfect-square particle count";
+    case PMC_E_COMM: return "pmc: communicator error";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pmc: unknown error";
+    }
+}
+
+int pmc_geometry_from_params(const pmc_params *pp, pmc_geometry *out)
+{
+    if (!pp || !out) return PMC_E_INVALID;
+    return derive_geometry(*pp, nullptr, nullptr, out);
+}
+
+int pmc_create(const pmc_params *pp, pmc_handle **out)
+{
+    if (!pp || !out) return PMC_E_INVALID;
+    pmc_params p;
+    DevGeom g0;
+    pmc_geometry pg0;
+    int grc = derive_geometry(*pp, &p, &g0, &pg0);
+    if (grc) return grc;
+    pmc_handle *h = (pmc_handle *)calloc(1, sizeof(pmc_handle));
+    if (!h) return PMC_E_INVALID;
+    h->p = p;
+    h->g = g0;
+    h->pg = pg0;
+    DevGeom &g = h->g;
     {   // fast path eligibility: the 3-neighbour-cell argument needs w >= 2 sigma with a margin
         // far above float rounding; tiny boxes would need more than one periodic image
         Geom4 &q = h->g4;
@@ -663,6 +683,144 @@ int pmc_run_host(pmc_handle *h, const float *r_host, uint64_t sweep0, int n_swee
     CK(cudaMemcpyAsync(disk_host, h->run_disk, pmc_disk_bytes(h), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(n_host, h->run_n, pmc_n_bytes(h), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ initial configurations / trajectory / checkpoint
+// Random sequential addition (BASELINE north_star: "synthetic random-sequential-addition initial
+// configurations").  RSA of disks jams at phi ~ 0.547, so this serves the dilute
+// configurations; dense ones start from the reference's lattice (init_r).  Serial host code, a
+// pure function of (params, seed): every rank of a slab run generates the same configuration.
+int pmc_rsa_host(const pmc_params *pp, uint64_t seed, float *r_host, int64_t *attempts_out)
+{
+    if (!pp || !r_host) return PMC_E_INVALID;
+    pmc_geometry pg;
+    int rc = pmc_geometry_from_params(pp, &pg);
+    if (rc) return rc;
+    const long long N = pp->n_particles;
+    const double L = (double)pg.cps * (double)pg.w, sig = (double)pp->sigma_d * (1.0 + 1e-5), sig2 = sig * sig;
+    // insertion grid: cells of width >= sigma, at most 4 disks each (a 1 x 1 sigma square holds <= 4 centres)
+    const int gc = (int)floor(L / sig);
+    if (gc < 3) return PMC_E_INVALID;
+    const double gw = L / gc;
+    std::vector<int> cnt((size_t)gc * gc, 0);
+    std::vector<float> gx((size_t)gc * gc * 4), gy((size_t)gc * gc * 4);
+    long long placed = 0, attempts = 0;
+    const long long max_attempts = N * 2000;
+    while (placed < N && attempts < max_attempts) {
+        uint32_t w4[4];
+        host_philox(0xFFFFFFFEu, (uint32_t)attempts, (uint32_t)((uint64_t)attempts >> 32), 3u << 16, seed, w4);
+        attempts++;
+        // 53-bit uniforms in [0, 1) -> positions in (-L/2, L/2], stored as float
+        const double u = ((double)(((uint64_t)w4[0] << 21) ^ (w4[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double v = ((double)(((uint64_t)w4[2] << 21) ^ (w4[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const float xf = (float)(L * 0.5 - u * L), yf = (float)(L * 0.5 - v * L);
+        const double x = xf, y = yf;
+        if (!(x > -L * 0.5 + 1e-6 * L) || !(y > -L * 0.5 + 1e-6 * L) || x > L * 0.5 || y > L * 0.5) continue;
+        int cx = (int)floor((x + L * 0.5) / gw), cy = (int)floor((y + L * 0.5) / gw);
+        cx = cx < 0 ? 0 : (cx >= gc ? gc - 1 : cx); cy = cy < 0 ? 0 : (cy >= gc ? gc - 1 : cy);
+        bool ok = true;
+        for (int dy = -1; dy <= 1 && ok; dy++)
+            for (int dx = -1; dx <= 1 && ok; dx++) {
+                int nx = cx + dx, ny = cy + dy;
+                double sx = 0.0, sy = 0.0;
+                if (nx < 0) { nx += gc; sx = -L; } else if (nx >= gc) { nx -= gc; sx = L; }
+                if (ny < 0) { ny += gc; sy = -L; } else if (ny >= gc) { ny -= gc; sy = L; }
+                const size_t c = (size_t)ny * gc + nx;
+                for (int k = 0; k < cnt[c]; k++) {
+                    const double ddx = (double)gx[c * 4 + k] + sx - x, ddy = (double)gy[c * 4 + k] + sy - y;
+                    if (ddx * ddx + ddy * ddy < sig2) { ok = false; break; }
+                }
+            }
+        const size_t c = (size_t)cy * gc + cx;
+        if (!ok || cnt[c] >= 4) continue;
+        gx[c * 4 + cnt[c]] = xf; gy[c * 4 + cnt[c]] = yf; cnt[c]++;
+        r_host[placed] = xf; r_host[placed + N] = yf;
+        placed++;
+    }
+    if (attempts_out) *attempts_out = attempts;
+    return placed == N ? 0 : PMC_E_UNSUPPORTED;     // jammed: phi too high for RSA
+}
+
+// One frame in the reference's trajectory format (create_dump kernel.cu:510-536, sample
+// dumpR3.txt): LAMMPS / OVITO text, ids re-enumerated per frame by disk_to_r (kernel.cu:497-507),
+// z = 0 in 2-D.  append = 0 truncates the file first.
+int pmc_write_dump(pmc_handle *h, const float *d_disk, const int16_t *d_n, const char *path, int timestep, int append)
+{
+    if (!h || !d_disk || !d_n || !path) return PMC_E_INVALID;
+    const long long N = h->p.n_particles;
+    std::vector<float> r((size_t)2 * N);
+    int64_t found = 0;
+    int rc = pmc_disk_to_r_host(h, d_disk, d_n, r.data(), &found);
+    if (rc) return rc;
+    FILE *fp = fopen(path, append ? "a" : "w");
+    if (!fp) return PMC_E_INVALID;
+    const long long np = found < N ? found : N;
+    const float hl = h->g.half_L;
+    fprintf(fp, "ITEM: TIMESTEP \n%i\nITEM: NUMBER OF ATOMS\n%lld\nITEM: BOX BOUNDS\n%f %f\n%f %f\n%f %f\nITEM: ATOMS id type x y z ix iy iz\n",
+            timestep, np, -hl, hl, -hl, hl, -0.5f, 0.5f);
+    for (long long j = 0; j < np; j++)
+        fprintf(fp, "%lld %lld %f %f %f 0 0 0\n", j + 1, j + 1, r[j], r[j + N], 0.0f);
+    fclose(fp);
+    return 0;
+}
+
+// Binary checkpoint / restart of (params, sweep, counters, disk, n): the reference has none
+// (SURVEY section 5); needed for long equation-of-state runs.
+struct CkptHeader {
+    char magic[8];
+    uint32_t version, nmax;
+    pmc_params params;
+    uint64_t sweep, trials, accepted, lost;
+    uint64_t disk_bytes, n_bytes;
+};
+
+int pmc_save_checkpoint(pmc_handle *h, const float *d_disk, const int16_t *d_n, uint64_t sweep, const char *path)
+{
+    if (!h || !d_disk || !d_n || !path) return PMC_E_INVALID;
+    CkptHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "PMCB200", 8);
+    hd.version = 1; hd.nmax = PMC_NMAX; hd.params = h->p; hd.sweep = sweep;
+    uint32_t status;
+    int rc = pmc_get_counters(h, &hd.trials, &hd.accepted, &hd.lost, &status);
+    if (rc) return rc;
+    hd.disk_bytes = pmc_disk_bytes(h); hd.n_bytes = pmc_n_bytes(h);
+    std::vector<char> buf(hd.disk_bytes + hd.n_bytes);
+    CK(cudaMemcpyAsync(buf.data(), d_disk, hd.disk_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(buf.data() + hd.disk_bytes, d_n, hd.n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return PMC_E_INVALID;
+    bool ok = fwrite(&hd, sizeof(hd), 1, fp) == 1 && fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? 0 : PMC_E_INVALID;
+}
+
+int pmc_load_checkpoint(pmc_handle *h, const char *path, float *d_disk, int16_t *d_n, uint64_t *sweep)
+{
+    if (!h || !d_disk || !d_n || !path) return PMC_E_INVALID;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return PMC_E_INVALID;
+    CkptHeader hd;
+    if (fread(&hd, sizeof(hd), 1, fp) != 1 || memcmp(hd.magic, "PMCB200", 8) != 0 || hd.version != 1) { fclose(fp); return PMC_E_INVALID; }
+    // the state only makes sense for the geometry and RNG stream it was written with
+    const pmc_params &a = hd.params, &b = h->p;
+    if (a.n_particles != b.n_particles || a.phi != b.phi || a.sigma_d != b.sigma_d || a.cell_w != b.cell_w ||
+        a.nmax != b.nmax || a.cps_multiple != b.cps_multiple || a.rank != b.rank || a.n_ranks != b.n_ranks ||
+        hd.disk_bytes != pmc_disk_bytes(h) || hd.n_bytes != pmc_n_bytes(h)) { fclose(fp); return PMC_E_INVALID; }
+    std::vector<char> buf(hd.disk_bytes + hd.n_bytes);
+    bool ok = fread(buf.data(), 1, buf.size(), fp) == buf.size();
+    fclose(fp);
+    if (!ok) return PMC_E_INVALID;
+    CK(cudaMemcpyAsync(d_disk, buf.data(), hd.disk_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_n, buf.data() + hd.disk_bytes, hd.n_bytes, cudaMemcpyHostToDevice, h->stream));
+    Counters c;
+    memset(&c, 0, sizeof(c));
+    c.trials = hd.trials; c.accepted = hd.accepted; c.lost = hd.lost;
+    CK(cudaMemcpyAsync(h->d_ctr, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (sweep) *sweep = hd.sweep;
     return 0;
 }
 

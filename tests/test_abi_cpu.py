@@ -86,3 +86,37 @@ def test_c_driver_runs_the_reference_protocol(built):
     out = subprocess.run([exe, "16384", "6"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "fused_equals_per_call=1" in out.stdout
+
+
+# ---------------------------------------------------------------- host-only entry points (no GPU needed)
+@pytest.mark.parametrize("N,phi,cps,mult", [(4096, 0.70, 32, 2), (2 ** 20, 0.70, 542, 2), (2 ** 24, 0.70, 2168, 2),
+                                            (2 ** 24, 0.716, 2144, 2), (2 ** 28, 0.70, 8672, 16), (2 ** 22, 0.30, 1656, 2)])
+def test_geometry_from_params_matches_survey_table_and_oracle(built, N, phi, cps, mult):
+    import pmc_b200
+    from oracle import oracle as O
+    g = pmc_b200.geometry_from_params(N, phi=phi, cps_multiple=mult)
+    o = O.Oracle(N, phi=phi, cps_multiple=mult)
+    assert g.cps == cps == o.cps
+    assert g.w == o.g.w and g.L == o.g.L and g.n_cells == cps * cps
+
+
+def test_rsa_host_is_deterministic_and_overlap_free(built):
+    """BASELINE north_star: random-sequential-addition initial configurations (dilute regime)."""
+    import numpy as np
+    import pmc_b200
+    from oracle import oracle as O
+    N = 2 ** 14
+    r1, a1 = pmc_b200.rsa_host(N, seed=7, phi=0.30)
+    r2, a2 = pmc_b200.rsa_host(N, seed=7, phi=0.30)
+    r3, _ = pmc_b200.rsa_host(N, seed=8, phi=0.30)
+    assert np.array_equal(r1, r2) and a1 == a2 and not np.array_equal(r1, r3)
+    assert a1 > N                                   # some insertions were rejected
+    o = O.Oracle(N, phi=0.30, move_delta=0.4)
+    disk, n = o.assign(r1)
+    chk = o.check(disk, n)
+    assert o.lost == 0 and chk["total"] == N and chk["overlaps"] == 0 and chk["out_of_cell"] == 0
+    assert float(chk["min_d2"]) >= 1.0
+    # RSA jams near phi = 0.547 (SURVEY H6): a dense request is refused, not looped on forever
+    with pytest.raises(pmc_b200.PmcError) as ei:
+        pmc_b200.rsa_host(1024, seed=1, phi=0.62)
+    assert ei.value.code == -2

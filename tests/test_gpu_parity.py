@@ -274,3 +274,88 @@ def test_assign_and_shift_cells_match_the_reference_kernels_on_gpu(seed):
     for step in gold["steps"][1:]:
         mc.shift_cells(disk, n, step["f"], float(np.float32(step["d"])))
         _assert_matches_reference_step(o, disk.cpu().numpy(), n.cpu().numpy(), step)
+
+
+# ---------------------------------------------------------------- RSA start, trajectory dump, checkpoint
+def test_rsa_start_sweeps_bit_exact():
+    """Dilute regime (BASELINE config 5): RSA initial configuration, empty cells, large moves."""
+    mc, o = pair(2 ** 16, phi=0.30, move_delta=0.4)
+    r = mc.rsa(seed=5)
+    disk, n = mc.assign(r)
+    odisk, on = o.assign(r.cpu().numpy())
+    assert_same_state(disk, n, odisk, on)
+    assert int((on == 0).sum()) > 0                  # the sparse path is exercised
+    mc.sweep(disk, n, 0, 6)
+    o.sweep(odisk, on, 0, 6)
+    assert_same_state(disk, n, odisk, on)
+    c = mc.counters()
+    assert (c["trials"], c["accepted"]) == (o.trials.value, o.accepted.value)
+    assert c["trials"] < 6 * 4 * o.n_cells           # empty cells perform no trials (subsweep.h:252-254)
+
+
+def test_dump_matches_the_reference_format(tmp_path):
+    """create_dump (kernel.cu:510-536): same header lines and row format as dumpR3.txt."""
+    mc, o = pair(4096)
+    disk, n = mc.assign(mc.init_r())
+    path = str(tmp_path / "dump.txt")
+    mc.write_dump(disk, n, path, timestep=0)
+    mc.sweep(disk, n, 0, 2)
+    mc.write_dump(disk, n, path, timestep=1, append=True)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "ITEM: TIMESTEP " and lines[1] == "0" and lines[2] == "ITEM: NUMBER OF ATOMS"
+    assert lines[3] == "4096" and lines[4] == "ITEM: BOX BOUNDS"
+    assert lines[8] == "ITEM: ATOMS id type x y z ix iy iz"
+    first = lines[9].split()
+    assert first[:2] == ["1", "1"] and first[5:] == ["0", "0", "0"] and len(first) == 8
+    frame = 9 + 4096
+    assert lines[frame] == "ITEM: TIMESTEP " and lines[frame + 1] == "1"
+    xy = np.array([[float(v) for v in ln.split()[2:4]] for ln in lines[9:9 + 4096]])
+    hl = o.g.L / 2
+    assert xy.min() > -hl - 1e-3 and xy.max() <= hl + 1e-3
+
+
+def test_checkpoint_restart_continues_the_same_trajectory(tmp_path):
+    mc, o = pair(2 ** 14)
+    disk, n = mc.assign(mc.init_r())
+    mc.sweep(disk, n, 0, 4)
+    path = str(tmp_path / "state.ckpt")
+    mc.save_checkpoint(disk, n, 4, path)
+    mc.sweep(disk, n, 4, 3)
+    import pmc_b200
+    mc2 = pmc_b200.ParallelMC(2 ** 14, **KW)
+    d2, n2, sweep = mc2.load_checkpoint(path)
+    assert sweep == 4
+    mc2.sweep(d2, n2, sweep, 3)
+    assert_same_state(d2, n2, disk.cpu().numpy(), n.cpu().numpy())
+    assert mc2.counters() == mc.counters()
+    other = pmc_b200.ParallelMC(2 ** 16, **KW)
+    with pytest.raises(pmc_b200.PmcError):
+        other.load_checkpoint(path)                   # geometry mismatch is refused
+
+
+# ---------------------------------------------------------------- observables against the hard-disk equation of state
+@pytest.mark.parametrize("phi,delta", [(0.30, 0.4), (0.50, 0.2)])
+def test_pressure_from_contact_value_matches_the_fluid_equation_of_state(phi, delta):
+    """beta P / rho = 1 + 2 phi g(sigma+) from the g(r) histogram, against Henderson's hard-disk
+    equation of state Z = (1 + phi^2 / 8) / (1 - phi)^2 (accurate to ~1 % in the fluid).
+    Tolerance 3 %: statistical error of 40 samples of 65 536 disks plus the EOS's own error."""
+    import pmc_b200
+    N = 2 ** 16
+    mc = pmc_b200.ParallelMC(N, phi=phi, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=delta, seed=99)
+    disk, n = mc.assign(mc.rsa(seed=11) if phi < 0.5 else mc.init_r())
+    mc.sweep(disk, n, 0, 3000)
+    nb, rmax = 200, float(mc.geom.w) * 0.999
+    hist = np.zeros(nb, dtype=np.uint64)
+    sweep, samples = 3000, 40
+    for _ in range(samples):
+        mc.sweep(disk, n, sweep, 50)
+        sweep += 50
+        hist += mc.gr_hist(disk, n, rmax, nb)
+    g, gc, z = mc.pressure_from_hist(hist, rmax, samples)
+    z_eos = (1 + phi * phi / 8) / (1 - phi) ** 2
+    chk = mc.check(disk, n)
+    assert chk["total"] == N and chk["out_of_cell"] == 0
+    assert abs(z - z_eos) < 0.03 * z_eos, (z, z_eos, gc)
+    assert g[: int(0.95 / (rmax / nb))].sum() == 0       # no pair inside the core
+    c = mc.counters()
+    assert 0.2 < c["accepted"] / c["trials"] < 0.8
