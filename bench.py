@@ -264,7 +264,7 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if fast:
         ms_per_launch = kernel_ms / kernel_launches     # events bracket the S sweep kernels of each call
-        kname = "sweep4_kernel<24,40,2> (one launch = one MC sweep: 4 colours + shiftCells)"
+        kname = "sweep4_kernel<24|26,24,3> (one launch = one MC sweep: 4 colours + shiftCells)"
     else:
         ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
         kname = "sweep_tile_kernel<4,26,32,320,2,*> (generic path)"

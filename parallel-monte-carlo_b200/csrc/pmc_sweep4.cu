@@ -609,7 +609,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-// tile configurations (PMC_TILE4 selects; 0 is the tuned default)
+// tile configurations (PMC_TILE4 selects; 1 is the tuned default)
 struct TileCfg { int tx, ty, hb, syb, h; };
 template <int TX, int TY> constexpr TileCfg cfg_of() { return { TX, TY, Tile4<TX, TY>::HB, Tile4<TX, TY>::SYB, Tile4<TX, TY>::H }; }
 constexpr TileCfg kCfgs[] = { cfg_of<24, 40>(), cfg_of<24, 24>(), cfg_of<24, 32>(), cfg_of<24, 48>() };
@@ -622,8 +622,8 @@ int tile_index()
 {
     static const int idx = [] {
         const char *e = getenv("PMC_TILE4");
-        const int i = e ? atoi(e) : 0;
-        return (i >= 0 && i < (int)(sizeof(kCfgs) / sizeof(kCfgs[0]))) ? i : 0;
+        const int i = e ? atoi(e) : 1;      // tuned default: 24 / 26 x 24 tiles, 3 CTAs per SM
+        return (i >= 0 && i < (int)(sizeof(kCfgs) / sizeof(kCfgs[0]))) ? i : 1;
     }();
     return idx;
 }
@@ -656,7 +656,7 @@ void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS)
     const int gx = (cps + c.tx - 1) / c.tx, gy = (rows + c.ty - 1) / c.ty;
     // last staged column: kMX + (gx-1)*TX - H - 1 (rounded down to even) + 2*HB - 1
     int cols = kMX + (gx - 1) * c.tx - c.h + 2 * c.hb + 2;
-    if (tile_index() == 0) {
+    if (tile_index() <= 1) {
         const int gxw = (cps + kCfgWideY.tx - 1) / kCfgWideY.tx;
         const int colsw = kMX + (gxw - 1) * kCfgWideY.tx - kCfgWideY.h + 2 * kCfgWideY.hb + 2;
         cols = colsw > cols ? colsw : cols;
@@ -708,7 +708,9 @@ cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout,
                               Counters *ctr, cudaStream_t st)
 {
     switch (tile_index()) {
-    case 1: return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st);
+    case 1:
+        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st);
+        return launch_cfg<26, 24, 3>(g, tmap_in, dout, a, ctr, st);
     case 2: return launch_cfg<24, 32, 2>(g, tmap_in, dout, a, ctr, st);
     case 3: return launch_cfg<24, 48, 1>(g, tmap_in, dout, a, ctr, st);
     default:
