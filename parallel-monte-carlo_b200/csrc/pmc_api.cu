@@ -89,6 +89,9 @@ struct pmc_handle {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *ktime_pending;
     double ktime_ms;
     long long ktime_launches, ktime_pending_launches;
+    // slab runs: ghost rows travel on a side stream while the interior tile rows are computed
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_boundary, ev_exchanged;
     alignas(64) unsigned char v4_tmap[2][128];
 };
 
@@ -250,6 +253,7 @@ int pmc_destroy(pmc_handle *h)
         for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         delete h->ktime_pending;
     }
+    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_boundary); cudaEventDestroy(h->ev_exchanged); }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     free(h);
     return 0;
@@ -396,7 +400,7 @@ extern "C" int pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launche
 static size_t v4_bytes(const pmc_handle *h) { return (size_t)2 * h->g4.CH * h->g4.ROWS * 4 * sizeof(float4); }
 
 // slab ring on the internal layout: whole rows (4 planes x 2 parities x CH chunks) are contiguous
-static int v4_exchange_async(pmc_handle *h, float4 *buf)
+static int v4_exchange_async(pmc_handle *h, float4 *buf, cudaStream_t st)
 {
     if (h->p.n_ranks <= 1) return 0;
     if (!h->comm) return PMC_E_COMM;
@@ -406,10 +410,10 @@ static int v4_exchange_async(pmc_handle *h, float4 *buf)
     char *B = (char *)buf;
     int rc = 0;
     rc |= g_nccl.GroupStart();
-    rc |= g_nccl.Send(B + (size_t)kMY * rp, blk, ncclInt8, lower, h->comm, h->stream);
-    rc |= g_nccl.Send(B + (size_t)rows * rp, blk, ncclInt8, upper, h->comm, h->stream);
-    rc |= g_nccl.Recv(B + (size_t)(kMY + rows) * rp, blk, ncclInt8, upper, h->comm, h->stream);
-    rc |= g_nccl.Recv(B, blk, ncclInt8, lower, h->comm, h->stream);
+    rc |= g_nccl.Send(B + (size_t)kMY * rp, blk, ncclInt8, lower, h->comm, st);
+    rc |= g_nccl.Send(B + (size_t)rows * rp, blk, ncclInt8, upper, h->comm, st);
+    rc |= g_nccl.Recv(B + (size_t)(kMY + rows) * rp, blk, ncclInt8, upper, h->comm, st);
+    rc |= g_nccl.Recv(B, blk, ncclInt8, lower, h->comm, st);
     rc |= g_nccl.GroupEnd();
     return rc ? PMC_E_COMM : 0;
 }
@@ -433,6 +437,14 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     }
     int cur = 0;
     static const int dbg = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
+    static const int overlap = [] { const char *e = getenv("PMC_OVERLAP"); return e ? atoi(e) : 1; }();
+    if (h->p.n_ranks > 1 && !h->comm_stream) {
+        int prio_lo = 0, prio_hi = 0;               // the exchange must not queue behind the interior tiles
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
+        CK(cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_exchanged, cudaEventDisableTiming));
+    }
     static const int pf_ahead = [] { const char *e = getenv("PMC_PREFETCH"); return e ? atoi(e) : 296; }();
     cudaEvent_t k0, k1;
     CK(cudaEventCreate(&k0));
@@ -455,9 +467,24 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         a.shift_on = 1; a.shift_f = f; a.shift_d = d;
         a.dbg_skip = dbg;
         a.prefetch_ahead = pf_ahead;
-        CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream));
-        int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1]);
-        if (rc) return rc;
+        const int gy = pmc4_tile_rows(h->g4), ty = pmc4_tile_y();
+        // tile rows that hold one of the kMY owned rows next to a slab face
+        const int top0 = (h->g4.rows - kMY) / ty;
+        if (h->p.n_ranks > 1 && overlap && top0 > 1 && top0 < gy) {
+            // boundary tile rows first; their ghost-row exchange overlaps the interior rows
+            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 0, 1, top0, gy - top0));
+            CK(cudaEventRecord(h->ev_boundary, h->stream));
+            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 1, top0 - 1));
+            CK(cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+            int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1], h->comm_stream);
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_exchanged, h->comm_stream));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged, 0));
+        } else {
+            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream));
+            int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1], h->stream);
+            if (rc) return rc;
+        }
         cur ^= 1;
     }
     CK(cudaEventRecord(k1, h->stream));

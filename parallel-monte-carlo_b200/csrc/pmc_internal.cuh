@@ -45,6 +45,8 @@ struct SweepArgs {
     int shift_on;           // apply a pending shiftCells(f, d) while staging the tile
     int shift_f;
     float shift_d;
+    int by_off;             // fused fast path: first tile row of this launch (boundary / interior split of slab runs)
+    int by_n1, by_off2;     // grid rows >= by_n1 map to tile rows by_off2 + (row - by_n1) (second band)
     int prefetch_ahead;     // fused fast path: L2-prefetch the tile of block id + this (0 = off)
     int dbg_skip;           // profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store
 };
@@ -83,8 +85,11 @@ void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS);
 int pmc4_make_tensor_map(void *tmap_out128, const float4 *base, const Geom4 &g);
 cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out, cudaStream_t st);
 cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, float4 *disk, int16_t *n, cudaStream_t st);
+// tile rows [by0, by0 + nby) of one sweep (nby <= 0: all rows)
+// optional second band [by1, by1 + nby1) in the same launch
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
-                              Counters *ctr, cudaStream_t st);
+                              Counters *ctr, cudaStream_t st, int by0 = 0, int nby = 0, int by1 = 0, int nby1 = 0);
+int pmc4_tile_rows(const Geom4 &g);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ Philox4x32-10

@@ -387,6 +387,8 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
 
     const int tid = threadIdx.x;
     const int cps = g.cps;
+    // tile row (a launch may cover one or two bands of rows)
+    const int tby = (int)blockIdx.y < a.by_n1 ? (int)blockIdx.y + a.by_off : (int)blockIdx.y - a.by_n1 + a.by_off2;
 
     // this sweep's grid shift: the tile carries one extra row / column on the upstream side
     const bool do_shift = a.shift_on && !(a.dbg_skip & 2);
@@ -396,11 +398,11 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
     TileCtx t;
     t.RX = TX + 2 * H + exl + exh; t.RY = TY + 2 * H + eyl + eyh;
     t.rx0 = blockIdx.x * TX - H - exl;
-    t.ry0 = blockIdx.y * TY - H - eyl;
+    t.ry0 = tby * TY - H - eyl;
     const int X0 = t.rx0 + kMX, Y0 = t.ry0 + kMY;   // region (0, 0) in internal array coordinates (>= 0)
     t.xs = X0 & 1;
     t.ox0 = H + exl; t.oy0 = H + eyl;
-    t.nox = min(TX, cps - (int)blockIdx.x * TX); t.noy = min(TY, g.rows - (int)blockIdx.y * TY);
+    t.nox = min(TX, cps - (int)blockIdx.x * TX); t.noy = min(TY, g.rows - tby * TY);
 
     // ------------------------------------------------------------ stage the tile: 4 TMA boxes
     if (tid == 0) {
@@ -413,7 +415,8 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
             // warm L2 for the tile a CTA slot freed by this wave will stage (blocks are issued in order)
             const int nb = blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
             if (nb < (int)(gridDim.x * gridDim.y)) {
-                const int by2 = nb / gridDim.x, bx2 = nb - by2 * gridDim.x;
+                const int gr2 = nb / gridDim.x, bx2 = nb - gr2 * gridDim.x;
+                const int by2 = gr2 < a.by_n1 ? gr2 + a.by_off : gr2 - a.by_n1 + a.by_off2;
                 const int X2 = bx2 * TX - H - exl + kMX, Y2 = by2 * TY - H - eyl + kMY;
 #pragma unroll
                 for (int p = 0; p < 4; p++) tma_prefetch_4d(&tmap, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
@@ -466,7 +469,7 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         constexpr int HX = TX / 2, RSTEP = THREADS / (8 * HX);   // threads beyond RSTEP * 8 * HX do not store
         const int h = tid % HX, pr = (tid / HX) & 1, pl = (tid / (2 * HX)) & 3, rg = tid / (8 * HX);
         const int ox = 2 * h + pr;                                  // owned column (parity == internal column parity)
-        const int ux = blockIdx.x * TX + ox, uy0 = blockIdx.y * TY;
+        const int ux = blockIdx.x * TX + ox, uy0 = tby * TY;
         if (ox < t.nox && rg < RSTEP) {
             const int is = t.ox0 + ox + t.xs;
             const float4 *cell0 = sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH;
@@ -629,7 +632,8 @@ int tile_index()
 }
 
 template <int TX, int TY, int MINB>
-cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a, Counters *ctr, cudaStream_t st)
+cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a_in, Counters *ctr,
+                       cudaStream_t st, int by0, int nby, int by1, int nby1)
 {
     using TL = Tile4<TX, TY>;
     auto kern = sweep4_kernel<TX, TY, MINB>;
@@ -639,12 +643,22 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((g.cps + TX - 1) / TX, (g.rows + TY - 1) / TY);
+    const int gy = (g.rows + TY - 1) / TY;
+    SweepArgs a = a_in;
+    a.by_off = by0;
+    if (nby <= 0) { a.by_off = 0; nby = gy; }
+    if (a.by_off + nby > gy) nby = gy - a.by_off;
+    if (nby <= 0) return cudaSuccess;
+    a.by_n1 = nby; a.by_off2 = by1;
+    if (nby1 < 0 || by1 + nby1 > gy) nby1 = 0;
+    dim3 grid((g.cps + TX - 1) / TX, nby + nby1);
     kern<<<grid, TL::THREADS, TL::SMEM, st>>>(*(const CUtensorMap *)tmap_in, dout, g, a, ctr);
     return cudaGetLastError();
 }
 
 }  // namespace
+
+int pmc4_tile_rows(const Geom4 &g) { const int ty = kCfgs[tile_index()].ty; return (g.rows + ty - 1) / ty; }
 
 int pmc4_tile_x() { return kCfgs[tile_index()].tx; }
 int pmc4_tile_y() { return kCfgs[tile_index()].ty; }
@@ -705,16 +719,16 @@ cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, floa
 }
 
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
-                              Counters *ctr, cudaStream_t st)
+                              Counters *ctr, cudaStream_t st, int by0, int nby, int by1, int nby1)
 {
     switch (tile_index()) {
     case 1:
-        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st);
-        return launch_cfg<26, 24, 3>(g, tmap_in, dout, a, ctr, st);
-    case 2: return launch_cfg<24, 32, 2>(g, tmap_in, dout, a, ctr, st);
-    case 3: return launch_cfg<24, 48, 1>(g, tmap_in, dout, a, ctr, st);
+        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
+        return launch_cfg<26, 24, 3>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
+    case 2: return launch_cfg<24, 32, 2>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
+    case 3: return launch_cfg<24, 48, 1>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
     default:
-        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 40, 2>(g, tmap_in, dout, a, ctr, st);
-        return launch_cfg<26, 40, 2>(g, tmap_in, dout, a, ctr, st);
+        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 40, 2>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
+        return launch_cfg<26, 40, 2>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
     }
 }
