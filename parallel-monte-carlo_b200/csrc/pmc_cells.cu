@@ -59,9 +59,14 @@ __device__ __forceinline__ int local_row(int gy, const DevGeom &g)
 }
 
 // pass 1: one thread per particle: cell id, atomic arrival rank, remember the particle index
+// Arrivals beyond the 8th go to a small global list, so that an overflowing cell keeps its 8
+// LOWEST particle indices (what a scan over atoms 0..N-1, start.cu:133-140, keeps when it stops
+// writing at nmax) whatever order the atomics resolve in.
+constexpr unsigned kOvfCap = 1u << 20;
+
 __global__ void assign_rank_kernel(const float *__restrict__ r, DevGeom g,
                                    unsigned *__restrict__ cnt32, unsigned *__restrict__ idx_tmp,
-                                   Counters *ctr)
+                                   uint2 *__restrict__ ovf, unsigned *__restrict__ ovf_count, Counters *ctr)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= g.n_particles) return;
@@ -77,6 +82,10 @@ __global__ void assign_rank_kernel(const float *__restrict__ r, DevGeom g,
     long long cell = (long long)lr * g.cps + cx;
     unsigned s = atomicAdd(cnt32 + cell, 1u);
     if (s < PMC_NMAX) idx_tmp[cell * PMC_NMAX + s] = (unsigned)i;
+    else {
+        const unsigned k = atomicAdd(ovf_count, 1u);
+        if (k < kOvfCap) ovf[k] = make_uint2((unsigned)cell, (unsigned)i);
+    }
 }
 
 __device__ __forceinline__ void cswap(unsigned &a, unsigned &b)
@@ -90,6 +99,7 @@ __device__ __forceinline__ void cswap(unsigned &a, unsigned &b)
 __global__ void assign_fill_kernel(const float *__restrict__ r, DevGeom g,
                                    const unsigned *__restrict__ cnt32,
                                    const unsigned *__restrict__ idx_tmp,
+                                   const uint2 *__restrict__ ovf, const unsigned *__restrict__ ovf_count,
                                    float4 *__restrict__ disk, int16_t *__restrict__ n, Counters *ctr)
 {
     long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -115,6 +125,17 @@ __global__ void assign_fill_kernel(const float *__restrict__ r, DevGeom g,
     cswap(v[1], v[4]); cswap(v[3], v[6]);
     cswap(v[2], v[4]); cswap(v[3], v[5]);
     cswap(v[3], v[4]);
+    if (c32 > PMC_NMAX) {
+        // rare: merge the late arrivals, keep the 8 smallest indices (v stays sorted ascending)
+        const unsigned m = min(*ovf_count, kOvfCap);
+        for (unsigned k = 0; k < m; k++) {
+            const uint2 e = ovf[k];
+            if (e.x != (unsigned)cell || e.y >= v[7]) continue;
+            v[7] = e.y;
+            cswap(v[6], v[7]); cswap(v[5], v[6]); cswap(v[4], v[5]); cswap(v[3], v[4]);
+            cswap(v[2], v[3]); cswap(v[1], v[2]); cswap(v[0], v[1]);
+        }
+    }
     int lr = (int)(cell / g.cps), cx = (int)(cell - (long long)lr * g.cps);
     int cy = g.wrap_y ? lr : wrap_mod(g.row0 - g.ghost + lr, g.cps);
     float xs[8], ys[8];
@@ -340,19 +361,25 @@ cudaError_t pmc_launch_assign(const DevGeom &g, const float *d_r, float4 *disk, 
 {
     long long local_cells = (long long)g.local_rows * g.cps;
     unsigned *cnt32 = nullptr, *idx_tmp = nullptr;
-    cudaError_t e = cudaMallocAsync(&cnt32, local_cells * sizeof(unsigned), st);
+    uint2 *ovf = nullptr;
+    // cnt32[local_cells] is followed by the overflow-list counter (zeroed by the same memset)
+    cudaError_t e = cudaMallocAsync(&cnt32, (local_cells + 1) * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    e = cudaMallocAsync(&idx_tmp, local_cells * PMC_NMAX * sizeof(unsigned), st);
+    e = cudaMallocAsync(&ovf, (size_t)kOvfCap * sizeof(uint2), st);
     if (e != cudaSuccess) { cudaFreeAsync(cnt32, st); return e; }
-    cudaMemsetAsync(cnt32, 0, local_cells * sizeof(unsigned), st);
+    e = cudaMallocAsync(&idx_tmp, local_cells * PMC_NMAX * sizeof(unsigned), st);
+    if (e != cudaSuccess) { cudaFreeAsync(cnt32, st); cudaFreeAsync(ovf, st); return e; }
+    cudaMemsetAsync(cnt32, 0, (local_cells + 1) * sizeof(unsigned), st);
+    unsigned *ovf_count = cnt32 + local_cells;
     int threads = 256;
     long long b1 = (g.n_particles + threads - 1) / threads;
-    assign_rank_kernel<<<(unsigned)b1, threads, 0, st>>>(d_r, g, cnt32, idx_tmp, ctr);
+    assign_rank_kernel<<<(unsigned)b1, threads, 0, st>>>(d_r, g, cnt32, idx_tmp, ovf, ovf_count, ctr);
     long long b2 = (local_cells + threads - 1) / threads;
-    assign_fill_kernel<<<(unsigned)b2, threads, 0, st>>>(d_r, g, cnt32, idx_tmp, disk, n, ctr);
+    assign_fill_kernel<<<(unsigned)b2, threads, 0, st>>>(d_r, g, cnt32, idx_tmp, ovf, ovf_count, disk, n, ctr);
     e = cudaGetLastError();
     cudaFreeAsync(cnt32, st);
     cudaFreeAsync(idx_tmp, st);
+    cudaFreeAsync(ovf, st);
     return e;
 }
 

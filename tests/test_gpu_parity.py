@@ -359,3 +359,27 @@ def test_pressure_from_contact_value_matches_the_fluid_equation_of_state(phi, de
     assert g[: int(0.95 / (rmax / nb))].sum() == 0       # no pair inside the core
     c = mc.counters()
     assert 0.2 < c["accepted"] / c["trials"] < 0.8
+
+
+# ---------------------------------------------------------------- crowded cells: the 8-slot instantiation and dropped disks
+def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
+    """Small disks thrown uniformly at random: Poisson occupancy (mean 3), so cells with 7 and 8
+    disks occur in most tiles (the NS = 8 instantiation of the fused sweep, mixed with NS = 6
+    tiles), a few cells overflow in assign and in shiftCells (reported, identical to the oracle)."""
+    import torch
+    sigma, lam, N = 0.25, 3.0, 2 ** 16
+    phi = lam * np.pi * sigma * sigma / 16.0          # occupancy = 16 phi / (pi sigma^2) at w = 2
+    mc, o = pair(N, sigma_d=sigma, phi=float(phi), cell_w=2.0, move_delta=0.3)
+    rng = np.random.default_rng(12)
+    hl = np.float32(o.g.L / 2)
+    r = (rng.random((2, N), dtype=np.float32) * 2 - 1) * hl * np.float32(0.9999)
+    disk, n = mc.assign(torch.from_numpy(r).cuda())
+    odisk, on = o.assign(r)
+    assert_same_state(disk, n, odisk, on)
+    assert int((on >= 7).sum()) > 50 and int(on.max()) == 8
+    mc.sweep(disk, n, 0, 8)
+    o.sweep(odisk, on, 0, 8)
+    assert_same_state(disk, n, odisk, on)
+    c = mc.counters()
+    assert (c["trials"], c["accepted"], c["lost"]) == (o.trials.value, o.accepted.value, o.lost)
+    assert c["lost"] > 0 and c["status"] & 1
