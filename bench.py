@@ -234,7 +234,8 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     c = mc.counters()
-    kernel_ms, kernel_launches = mc.kernel_time()   # CUDA events around the fused sweep kernels alone
+    kernel_ms, kernel_launches = mc.kernel_time()   # CUDA events around the fused sweep kernels alone (per sweep)
+    gpu_launches = mc.launch_count()                # kernels actually launched in the timed region
     trials = torch.tensor([c["trials"], c["accepted"], c["lost"], c["status"]], dtype=torch.float64, device="cuda")
     tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist:
@@ -243,10 +244,7 @@ def main():
     ms = float(tmax.item())
     tot_trials, tot_acc, tot_lost, status = (float(x) for x in trials.tolist())
     value = tot_trials / (ms * 1e-3)
-    # per pmc_sweep call: layout import + S fused sweep kernels + layout export (fast path), or
-    # S fused kernels + 1 stand-alone shiftCells (generic path)
     fast = kernel_launches > 0
-    launches_per_step = S + 2 if fast else S + 1
     n_sweeps_timed = args.steps * S
 
     # invariants after the timed region (cheap, device side)
@@ -263,7 +261,8 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if fast:
-        ms_per_launch = kernel_ms / kernel_launches     # events bracket the S sweep kernels of each call
+        # CUDA events bracket the sweep kernels of each pmc_sweep call (import / export excluded)
+        ms_per_launch = kernel_ms / kernel_launches
         kname = "sweep4_kernel<24|26,24,3> (one launch = one MC sweep: 4 colours + shiftCells)"
     else:
         ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
@@ -335,7 +334,7 @@ def main():
             "invariants": {"particles": total_particles, "out_of_cell": int(chk_t[1].item()),
                            "overlaps_below_sigma": int(chk_t[2].item()), "min_d2": chk["min_d2"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(args.steps * launches_per_step),
+            "gpu_launches": int(gpu_launches),
         }
         print(json.dumps(line), flush=True)
     if dist:

@@ -122,6 +122,8 @@ int  pmc_reset_counters(pmc_handle *h);
 /* device time (CUDA events on the handle's stream) spent inside the fused sweep kernels of
  * pmc_sweep since the last pmc_reset_counters, and how many were launched (measurement aid) */
 int  pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launches);
+/* CUDA kernels this handle launched since the last pmc_reset_counters */
+int  pmc_get_launch_count(pmc_handle *h, long long *launches);
 /* invariants: out[0]=sum n, out[1]=#coords outside (0,w], out[2]=#pairs closer than sigma_d,
  * out[3]=#unused slots without the sentinel; min_d2 = smallest squared pair distance */
 int  pmc_check(pmc_handle *h, const float *d_disk, const int16_t *d_n, int64_t out[4], float *min_d2);

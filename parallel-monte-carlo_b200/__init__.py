@@ -108,6 +108,7 @@ def lib():
                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     L.pmc_reset_counters.argtypes = [hp]
     L.pmc_get_kernel_time.argtypes = [hp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.pmc_get_launch_count.argtypes = [hp, C.POINTER(C.c_longlong)]
     L.pmc_check.argtypes = [hp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     L.pmc_gr_hist.argtypes = [hp, vp, vp, C.c_float, C.c_int, vp]
     L.pmc_pressure_from_hist.argtypes = [hp, vp, C.c_float, C.c_int, C.c_int64, vp,
@@ -130,7 +131,7 @@ EXPORTS = ["pmc_create", "pmc_destroy", "pmc_get_geometry", "pmc_r_bytes", "pmc_
            "pmc_n_bytes", "pmc_set_stream", "pmc_set_blocking", "pmc_synchronize",
            "pmc_error_string", "pmc_init_r", "pmc_assign", "pmc_subsweep", "pmc_shift_cells",
            "pmc_schedule", "pmc_colour_to_off", "pmc_sweep", "pmc_get_counters",
-           "pmc_reset_counters", "pmc_get_kernel_time", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
+           "pmc_reset_counters", "pmc_get_kernel_time", "pmc_get_launch_count", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
            "pmc_disk_to_r_host", "pmc_run_host", "pmc_geometry_from_params", "pmc_rsa_host",
            "pmc_write_dump", "pmc_save_checkpoint", "pmc_load_checkpoint", "pmc_comm_unique_id", "pmc_comm_init",
            "pmc_exchange_ghosts"]
@@ -254,6 +255,11 @@ class ParallelMC:
 
     def reset_counters(self):
         _ck(lib().pmc_reset_counters(self._h))
+
+    def launch_count(self):
+        nl = C.c_longlong()
+        _ck(lib().pmc_get_launch_count(self._h, C.byref(nl)))
+        return nl.value
 
     def kernel_time(self):
         """(ms, launches) of the fused sweep kernels since the last reset_counters()."""

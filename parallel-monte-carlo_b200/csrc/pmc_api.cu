@@ -92,6 +92,9 @@ struct pmc_handle {
     // slab runs: ghost rows travel on a side stream while the interior tile rows are computed
     cudaStream_t comm_stream;
     cudaEvent_t ev_boundary, ev_exchanged;
+    // persistent multi-sweep kernel: per-sweep arguments and per-tile completion flags
+    int *done_dev;
+    long long launches;         // kernels launched by this handle since the last pmc_reset_counters
     alignas(64) unsigned char v4_tmap[2][128];
 };
 
@@ -249,6 +252,7 @@ int pmc_destroy(pmc_handle *h)
     cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
     cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
     cudaFree(h->v4_buf[0]); cudaFree(h->v4_buf[1]);
+    cudaFree(h->done_dev);
     if (h->ktime_pending) {
         for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         delete h->ktime_pending;
@@ -300,14 +304,14 @@ int pmc_init_r(pmc_handle *h, float *d_r)
     long long N = h->p.n_particles;
     long long ns = (long long)floor(sqrt((double)N) + 0.5);
     if (ns * ns != N) return PMC_E_NOT_SQUARE;
-    CK(pmc_launch_init_r(h->g, d_r, h->stream));
+    CK(pmc_launch_init_r(h->g, d_r, h->stream)); h->launches += 1;
     return finish(h);
 }
 
 int pmc_assign(pmc_handle *h, const float *d_r, float *d_disk, int16_t *d_n)
 {
     if (!h || !d_r || !d_disk || !d_n) return PMC_E_INVALID;
-    CK(pmc_launch_assign(h->g, d_r, (float4 *)d_disk, d_n, h->d_ctr, h->stream));
+    CK(pmc_launch_assign(h->g, d_r, (float4 *)d_disk, d_n, h->d_ctr, h->stream)); h->launches += 2;
     return finish(h);
 }
 
@@ -376,7 +380,7 @@ int pmc_subsweep(pmc_handle *h, float *d_disk, int16_t *d_n, const int off[2], u
     a.offmask = (unsigned)off[0] | ((unsigned)off[1] << 1);
     a.sanitize_in = 1;
     a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
-    CK(pmc_launch_subsweep(h->g, (float4 *)d_disk, d_n, a, h->d_ctr, h->stream));
+    CK(pmc_launch_subsweep(h->g, (float4 *)d_disk, d_n, a, h->d_ctr, h->stream)); h->launches += 1;
     int rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
     if (rc) return rc;
     return finish(h);
@@ -388,7 +392,7 @@ int pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
     if (!(fabsf(d) <= 0.5f * h->g.w * 1.0001f)) return PMC_E_INVALID;   // shiftCells.h:7 contract
     int rc = ensure_scratch(h);
     if (rc) return rc;
-    CK(pmc_launch_shift(h->g, (const float4 *)d_disk, d_n, h->scratch_disk, h->scratch_n, f, d, h->d_ctr, h->stream));
+    CK(pmc_launch_shift(h->g, (const float4 *)d_disk, d_n, h->scratch_disk, h->scratch_n, f, d, h->d_ctr, h->stream)); h->launches += 1;
     CK(cudaMemcpyAsync(d_disk, h->scratch_disk, pmc_disk_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(d_n, h->scratch_n, pmc_n_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
@@ -430,9 +434,9 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
             h->v4_padded = 0;
         }
     const int ghost = h->g.ghost;
-    CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[0], h->stream));
+    CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[0], h->stream)); h->launches += 1;
     if (!h->v4_padded) {        // cells beyond the margins are never written again: make them valid once
-        CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[1], h->stream));
+        CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[1], h->stream)); h->launches += 1;
         h->v4_padded = 1;
     }
     int cur = 0;
@@ -450,7 +454,42 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     CK(cudaEventCreate(&k0));
     CK(cudaEventCreate(&k1));
     CK(cudaEventRecord(k0, h->stream));
-    for (int t = 0; t < n_sweeps; t++) {
+    int t_done = 0;
+    // EXPERIMENTAL, off by default: measured 0.48 ms / sweep against 0.34 ms for one launch per sweep at
+    // N = 2^24; kept selectable for the round-2 investigation
+    static const int persistent = [] { const char *e = getenv("PMC_PERSISTENT"); return e ? atoi(e) : 0; }();
+    const int kBatch = pmc4_step_capacity();
+    if (persistent && h->p.n_ranks == 1) {
+        // single GPU: batches of sweeps in ONE cooperative launch each (no per-sweep launch, no idle tail)
+        if (!h->done_dev) CK(cudaMalloc(&h->done_dev, (size_t)pmc4_tile_count(h->g4) * sizeof(int)));
+        std::vector<Pmc4Step> steps;
+        while (t_done < n_sweeps) {
+            const int nb = n_sweeps - t_done < kBatch ? n_sweeps - t_done : kBatch;
+            steps.resize(nb);
+            for (int k = 0; k < nb; k++) {
+                const uint64_t sweep = sweep0 + (uint64_t)(t_done + k);
+                int order[4], f;
+                float d;
+                pmc_schedule(h, sweep, order, &f, &d);
+                unsigned mask = 0;
+                for (int c = 0; c < 4; c++) {
+                    int off[2];
+                    pmc_colour_to_off(order[c], off);
+                    mask |= ((unsigned)off[0] | ((unsigned)off[1] << 1)) << (2 * c);
+                }
+                steps[k].offmask = mask; steps[k].sweep_lo = (unsigned)sweep; steps[k].sweep_hi = (unsigned)(sweep >> 32);
+                steps[k].shift_f = f; steps[k].shift_d = d;
+            }
+            cudaError_t pe = pmc4_launch_persistent(h->g4, h->v4_tmap[0], h->v4_tmap[1], h->v4_buf[0], h->v4_buf[1],
+                                                    steps.data(), nb, cur, h->done_dev, h->d_ctr, dbg, h->stream);
+            if (pe == cudaErrorNotSupported) { cudaGetLastError(); break; }
+            CK(pe);
+            h->launches += 2;                           // flag memset + the cooperative kernel
+            cur ^= (nb & 1);
+            t_done += nb;
+        }
+    }
+    for (int t = t_done; t < n_sweeps; t++) {
         const uint64_t sweep = sweep0 + (uint64_t)t;
         int order[4], f;
         float d;
@@ -472,16 +511,16 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         const int top0 = (h->g4.rows - kMY) / ty;
         if (h->p.n_ranks > 1 && overlap && top0 > 1 && top0 < gy) {
             // boundary tile rows first; their ghost-row exchange overlaps the interior rows
-            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 0, 1, top0, gy - top0));
+            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 0, 1, top0, gy - top0)); h->launches += 1;
             CK(cudaEventRecord(h->ev_boundary, h->stream));
-            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 1, top0 - 1));
+            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 1, top0 - 1)); h->launches += 1;
             CK(cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
             int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1], h->comm_stream);
             if (rc) return rc;
             CK(cudaEventRecord(h->ev_exchanged, h->comm_stream));
             CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged, 0));
         } else {
-            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream));
+            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream)); h->launches += 1;
             int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1], h->stream);
             if (rc) return rc;
         }
@@ -492,7 +531,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     h->ktime_pending->push_back(std::make_pair(k0, k1));
     h->ktime_pending_launches += n_sweeps;
     if (h->ktime_pending->size() > 4096) { double ms; long long nl; pmc_get_kernel_time(h, &ms, &nl); }
-    CK(pmc4_launch_export(h->g4, ghost, h->v4_buf[cur], (float4 *)d_disk, d_n, h->stream));
+    CK(pmc4_launch_export(h->g4, ghost, h->v4_buf[cur], (float4 *)d_disk, d_n, h->stream)); h->launches += 1;
     return finish(h);
 }
 
@@ -527,14 +566,14 @@ int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n
         a.shift_on = pend_on; a.shift_f = pend_f; a.shift_d = pend_d;
         a.sanitize_in = (t == 0);       // only the first kernel reads the caller's arrays
         { const char *dbg = getenv("PMC_DBG_SKIP"); a.dbg_skip = dbg ? atoi(dbg) : 0; }
-        CK(pmc_launch_fused_sweep(h->g, cur_d, cur_n, oth_d, oth_n, a, h->d_ctr, h->stream));
+        CK(pmc_launch_fused_sweep(h->g, cur_d, cur_n, oth_d, oth_n, a, h->d_ctr, h->stream)); h->launches += 1;
         rc = exchange_ghosts_async(h, oth_d, oth_n);
         if (rc) return rc;
         float4 *td = cur_d; cur_d = oth_d; oth_d = td;
         int16_t *tn = cur_n; cur_n = oth_n; oth_n = tn;
         pend_on = 1; pend_f = f; pend_d = d;
     }
-    CK(pmc_launch_shift(h->g, cur_d, cur_n, oth_d, oth_n, pend_f, pend_d, h->d_ctr, h->stream));
+    CK(pmc_launch_shift(h->g, cur_d, cur_n, oth_d, oth_n, pend_f, pend_d, h->d_ctr, h->stream)); h->launches += 1;
     rc = exchange_ghosts_async(h, oth_d, oth_n);
     if (rc) return rc;
     if (oth_d != (float4 *)d_disk) {
@@ -579,9 +618,18 @@ int pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launches)
     return 0;
 }
 
+// kernels this handle launched since the last pmc_reset_counters (bench.py's gpu_launches)
+int pmc_get_launch_count(pmc_handle *h, long long *launches)
+{
+    if (!h || !launches) return PMC_E_INVALID;
+    *launches = h->launches;
+    return 0;
+}
+
 int pmc_reset_counters(pmc_handle *h)
 {
     if (!h) return PMC_E_INVALID;
+    h->launches = 0;
     { double ms; long long nl; pmc_get_kernel_time(h, &ms, &nl); h->ktime_ms = 0.0; h->ktime_launches = 0; }
     CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
     return finish(h);
@@ -590,7 +638,7 @@ int pmc_reset_counters(pmc_handle *h)
 int pmc_check(pmc_handle *h, const float *d_disk, const int16_t *d_n, int64_t out[4], float *min_d2)
 {
     if (!h || !d_disk || !d_n || !out || !min_d2) return PMC_E_INVALID;
-    CK(pmc_launch_check(h->g, (const float4 *)d_disk, d_n, h->d_out4, h->d_min, h->stream));
+    CK(pmc_launch_check(h->g, (const float4 *)d_disk, d_n, h->d_out4, h->d_min, h->stream)); h->launches += 1;
     long long o[4];
     unsigned bits;
     CK(cudaMemcpyAsync(o, h->d_out4, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
@@ -612,7 +660,7 @@ int pmc_gr_hist(pmc_handle *h, const float *d_disk, const int16_t *d_n, float r_
         CK(cudaMalloc(&h->d_hist, (size_t)nbins * sizeof(unsigned long long)));
         h->hist_cap = nbins;
     }
-    CK(pmc_launch_gr_hist(h->g, (const float4 *)d_disk, d_n, r_max, nbins, h->d_hist, h->stream));
+    CK(pmc_launch_gr_hist(h->g, (const float4 *)d_disk, d_n, r_max, nbins, h->d_hist, h->stream)); h->launches += 1;
     CK(cudaMemcpyAsync(hist_host, h->d_hist, (size_t)nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;

@@ -90,6 +90,12 @@ cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, floa
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
                               Counters *ctr, cudaStream_t st, int by0 = 0, int nby = 0, int by1 = 0, int nby1 = 0);
 int pmc4_tile_rows(const Geom4 &g);
+int pmc4_tile_count(const Geom4 &g);
+struct Pmc4Step { unsigned offmask, sweep_lo, sweep_hi; int shift_f; float shift_d; };   // = StepArgs of pmc_sweep4.cu
+int pmc4_step_capacity();
+cudaError_t pmc4_launch_persistent(const Geom4 &g, const void *tmap0, const void *tmap1, float4 *buf0, float4 *buf1,
+                                   const void *steps_host, int n_steps, int src0, int *done_dev, Counters *ctr,
+                                   int dbg, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ Philox4x32-10

@@ -28,6 +28,7 @@
 #include "pmc_internal.cuh"
 #include <cuda.h>      // CUtensorMap type only; the encoder comes from cudaGetDriverEntryPoint
 #include <stdlib.h>
+#include <mutex>
 
 namespace {
 
@@ -296,7 +297,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
 }
 
 // ---- shiftCells(f, d) of this sweep for the owned cells, in place (plain plane order out)
-template <int NS, int TX, int TY>
+template <int NS, int TX, int TY, bool UNROLL>
 __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const SweepArgs &a, float w, int sdir,
                                            int tid, Counters *ctr)
 {
@@ -346,7 +347,9 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const S
     }
     __syncthreads();
     constexpr int KMAX = K0 > K1 ? K0 : K1;
-#pragma unroll
+    // UNROLL: the walk is unrolled (no register moves between iterations); the persistent kernel,
+    // which carries more live state, keeps it rolled to stay spill-free at 80 registers
+#pragma unroll(UNROLL ? KMAX : 1)
     for (int u = 0; u < KMAX; u++) {
         if (u < len) {
             const int i = i0 + u * di, j = j0 + u * dj;
@@ -375,20 +378,19 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const S
     __syncthreads();
 }
 
-template <int TX, int TY, int MINB>
-__global__ void __launch_bounds__(Tile4<TX, TY>::THREADS, MINB)
-sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dout, const Geom4 g,
-              const SweepArgs a, Counters *ctr)
+// ---- one tile of one sweep: stage, 4 colours, shiftCells, store.  tbx / tby = tile column / row;
+// `phase` = parity of the mbarrier phase this staging completes (the barrier is reused by
+// the persistent kernel); pf_* describe the launch grid for the L2 prefetch (pf_n = 0: none).
+template <int TX, int TY, bool UNROLL_SHIFT>
+__device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *__restrict__ dout, const Geom4 &g,
+                                             const SweepArgs &a, Counters *ctr, int tbx, int tby,
+                                             float4 *sm, uint64_t *mbar, unsigned phase,
+                                             unsigned &my_trials, unsigned &my_acc)
 {
     using TL = Tile4<TX, TY>;
     constexpr int H = TL::H, HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC, NAX = TL::NAX, THREADS = TL::THREADS;
-    extern __shared__ __align__(128) float4 sm[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + 4 * PLC);
-
     const int tid = threadIdx.x;
     const int cps = g.cps;
-    // tile row (a launch may cover one or two bands of rows)
-    const int tby = (int)blockIdx.y < a.by_n1 ? (int)blockIdx.y + a.by_off : (int)blockIdx.y - a.by_n1 + a.by_off2;
 
     // this sweep's grid shift: the tile carries one extra row / column on the upstream side
     const bool do_shift = a.shift_on && !(a.dbg_skip & 2);
@@ -397,20 +399,18 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
     const int eyl = (do_shift && a.shift_f == 1 && sdir < 0), eyh = (do_shift && a.shift_f == 1 && sdir > 0);
     TileCtx t;
     t.RX = TX + 2 * H + exl + exh; t.RY = TY + 2 * H + eyl + eyh;
-    t.rx0 = blockIdx.x * TX - H - exl;
+    t.rx0 = tbx * TX - H - exl;
     t.ry0 = tby * TY - H - eyl;
     const int X0 = t.rx0 + kMX, Y0 = t.ry0 + kMY;   // region (0, 0) in internal array coordinates (>= 0)
     t.xs = X0 & 1;
     t.ox0 = H + exl; t.oy0 = H + eyl;
-    t.nox = min(TX, cps - (int)blockIdx.x * TX); t.noy = min(TY, g.rows - tby * TY);
+    t.nox = min(TX, cps - tbx * TX); t.noy = min(TY, g.rows - tby * TY);
 
     // ------------------------------------------------------------ stage the tile: 4 TMA boxes
     if (tid == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(mbar, (unsigned)(4 * TL::PLB * 16));
 #pragma unroll
-        for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, &tmap, 4 * ((X0 - t.xs) >> 1), 0, p, Y0, mbar);
+        for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, tmap_p, 4 * ((X0 - t.xs) >> 1), 0, p, Y0, mbar);
         if (a.prefetch_ahead > 0) {
             // warm L2 for the tile a CTA slot freed by this wave will stage (blocks are issued in order)
             const int nb = blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
@@ -419,13 +419,13 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
                 const int by2 = gr2 < a.by_n1 ? gr2 + a.by_off : gr2 - a.by_n1 + a.by_off2;
                 const int X2 = bx2 * TX - H - exl + kMX, Y2 = by2 * TY - H - eyl + kMY;
 #pragma unroll
-                for (int p = 0; p < 4; p++) tma_prefetch_4d(&tmap, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
+                for (int p = 0; p < 4; p++) tma_prefetch_4d(tmap_p, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
             }
         }
-        mbar_wait(mbar, 0);     // one poller; the others observe the completed phase once
+        mbar_wait(mbar, phase);     // one poller; the others observe the completed phase once
     }
     __syncthreads();
-    mbar_wait(mbar, 0);
+    mbar_wait(mbar, phase);
 
     // does any staged cell hold 7 or 8 disks (x6 in use)?  Otherwise P3 is never needed.
     int big = 0;
@@ -437,7 +437,6 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
     const bool ns8 = __syncthreads_or(big) || (a.dbg_skip & 8);
 
     // ------------------------------------------------------------ the four sub-sweeps
-    unsigned my_trials = 0, my_acc = 0;
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
     if (!(a.dbg_skip & 1)) {
         if (!ns8) {
@@ -457,8 +456,8 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
 
     // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
     if (do_shift) {
-        if (!ns8) shift_pass<6, TX, TY>(sm, t, a, g.w, sdir, tid, ctr);
-        else shift_pass<8, TX, TY>(sm, t, a, g.w, sdir, tid, ctr);
+        if (!ns8) shift_pass<6, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
+        else shift_pass<8, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
     }
 
     // ------------------------------------------------------------ owned tile -> HBM (+ periodic images into the margins)
@@ -469,7 +468,7 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         constexpr int HX = TX / 2, RSTEP = THREADS / (8 * HX);   // threads beyond RSTEP * 8 * HX do not store
         const int h = tid % HX, pr = (tid / HX) & 1, pl = (tid / (2 * HX)) & 3, rg = tid / (8 * HX);
         const int ox = 2 * h + pr;                                  // owned column (parity == internal column parity)
-        const int ux = blockIdx.x * TX + ox, uy0 = tby * TY;
+        const int ux = tbx * TX + ox, uy0 = tby * TY;
         if (ox < t.nox && rg < RSTEP) {
             const int is = t.ox0 + ox + t.xs;
             const float4 *cell0 = sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH;
@@ -515,12 +514,117 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dou
         }
     }
 
-    // acceptance counts reduced warp-level, one atomic per warp (kernel.cu:228,413 accept_counter)
+}
+
+// acceptance counts reduced warp-level, one atomic per warp (kernel.cu:228,413 accept_counter)
+__device__ __forceinline__ void flush_counters(Counters *ctr, unsigned my_trials, unsigned my_acc)
+{
     my_trials = __reduce_add_sync(0xffffffffu, my_trials);
     my_acc = __reduce_add_sync(0xffffffffu, my_acc);
-    if ((tid & 31) == 0 && my_trials) {
+    if ((threadIdx.x & 31) == 0 && my_trials) {
         atomicAdd(&ctr->trials, (unsigned long long)my_trials);
         atomicAdd(&ctr->accepted, (unsigned long long)my_acc);
+    }
+}
+
+// ---- one launch = one sweep (slab runs, and the fallback of the persistent kernel)
+template <int TX, int TY, int MINB>
+__global__ void __launch_bounds__(Tile4<TX, TY>::THREADS, MINB)
+sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dout, const Geom4 g,
+              const SweepArgs a, Counters *ctr)
+{
+    using TL = Tile4<TX, TY>;
+    extern __shared__ __align__(128) float4 sm[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + 4 * TL::PLC);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // tile row (a launch may cover one or two bands of rows)
+    const int tby = (int)blockIdx.y < a.by_n1 ? (int)blockIdx.y + a.by_off : (int)blockIdx.y - a.by_n1 + a.by_off2;
+    unsigned my_trials = 0, my_acc = 0;
+    process_tile<TX, TY, true>(&tmap, dout, g, a, ctr, (int)blockIdx.x, tby, sm, mbar, 0u, my_trials, my_acc);
+    flush_counters(ctr, my_trials, my_acc);
+}
+
+// ---- persistent kernel: n_steps sweeps in ONE cooperative launch (single GPU).  CTA c owns
+// tiles c, c + G, c + 2G, ... of every sweep; there is no grid-wide barrier between sweeps:
+// a tile of sweep s starts as soon as the (up to 4 x 4, normally 3 x 3) tiles of sweep s-1
+// that produced its staged box - and that were the last readers of the cells it is about to
+// overwrite in the other ping-pong buffer - have published done[tile] >= s.  This removes the
+// per-sweep launch and the idle tail of the last partial wave (~5 % at N = 2^24).
+struct StepArgs { unsigned offmask, sweep_lo, sweep_hi; int shift_f; float shift_d; };
+constexpr int kStepCap = 1024;
+// per-sweep arguments of the batch in flight: constant memory, indexed by the (warp-uniform) sweep
+// counter, so they live in the uniform datapath instead of in vector registers
+__constant__ StepArgs c_steps[kStepCap];
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int TX, int TY, int MINB>
+__global__ void __launch_bounds__(Tile4<TX, TY>::THREADS, MINB)
+sweep4_persistent(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                  float4 *__restrict__ buf0, float4 *__restrict__ buf1, const Geom4 g,
+                  int n_steps, int src0, int *done, Counters *ctr, int dbg)
+{
+    using TL = Tile4<TX, TY>;
+    extern __shared__ __align__(128) float4 sm[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + 4 * TL::PLC);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int gx = (g.cps + TX - 1) / TX, gy = (g.rows + TY - 1) / TY, ntiles = gx * gy;
+    unsigned phase = 0;
+#pragma unroll 1
+    for (int s = 0; s < n_steps; s++) {
+        SweepArgs sa;
+        sa.offmask = c_steps[s].offmask; sa.sweep_lo = c_steps[s].sweep_lo; sa.sweep_hi = c_steps[s].sweep_hi;
+        sa.shift_on = 1; sa.shift_f = c_steps[s].shift_f; sa.shift_d = c_steps[s].shift_d;
+        sa.sanitize_in = 0; sa.by_off = 0; sa.by_n1 = 0x7fffffff; sa.by_off2 = 0; sa.prefetch_ahead = 0; sa.dbg_skip = dbg;
+        const int src = (src0 + s) & 1;
+#pragma unroll 1
+        for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
+            // every other sweep starts half a grid away: the tiles a CTA runs first never depend on
+            // the tiles the previous sweep finished last (first and last tile rows are periodic
+            // neighbours), so there is no idle tail between sweeps
+            int tile = it + ((s & 1) ? ntiles / 2 : 0);
+            tile -= tile >= ntiles ? ntiles : 0;
+            const int tby = tile / gx, tbx = tile - tby * gx;
+            if (s > 0 && tid < 16) {
+                // producers (sweep s-1) of every cell this tile stages or overwrites: the tiles under
+                // the four corner-ish columns / rows of the staged box, wrapped like the images
+                const int x0 = tbx * TX, y0 = tby * TY;
+                const int xl = min(x0 + TX, g.cps) - 1, yl = min(y0 + TY, g.rows) - 1;
+                const int sx = tid & 3, sy = tid >> 2;
+                int cx = sx == 0 ? x0 - kMX : (sx == 1 ? x0 : (sx == 2 ? xl : xl + kMX));
+                int cy = sy == 0 ? y0 - kMY : (sy == 1 ? y0 : (sy == 2 ? yl : yl + kMY));
+                cx += cx < 0 ? g.cps : 0; cx -= cx >= g.cps ? g.cps : 0;
+                cy += cy < 0 ? g.rows : 0; cy -= cy >= g.rows ? g.rows : 0;
+                const int *flag = done + (cy / TY) * gx + cx / TX;
+                while (ld_acquire(flag) < s) __nanosleep(64);
+            }
+            __syncthreads();
+            if (tid == 0) asm volatile("fence.proxy.async;" ::: "memory");   // the TMA reads what the producers stored
+            unsigned my_trials = 0, my_acc = 0;
+            process_tile<TX, TY, false>(src ? &tm1 : &tm0, src ? buf0 : buf1, g, sa, ctr, tbx, tby, sm, mbar, phase, my_trials, my_acc);
+            flush_counters(ctr, my_trials, my_acc);
+            phase ^= 1u;
+            __threadfence();            // this tile's stores are visible device-wide ...
+            __syncthreads();            // ... before thread 0 publishes it (also: smem is free for the next box)
+            if (tid == 0) st_release(done + tile, s + 1);
+        }
     }
 }
 
@@ -657,6 +761,65 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const 
 }
 
 }  // namespace
+
+// persistent multi-sweep launch (single GPU, default tiling): returns cudaErrorNotSupported when
+// the geometry does not qualify (the caller then launches one kernel per sweep)
+int pmc4_step_capacity() { return kStepCap; }
+
+// steps_host: n_steps Pmc4Step records (pageable is fine).  The constant bank is shared by every
+// handle of this process on this device: a launch waits for the previous batch to finish.
+cudaError_t pmc4_launch_persistent(const Geom4 &g, const void *tmap0, const void *tmap1, float4 *buf0, float4 *buf1,
+                                   const void *steps_host, int n_steps, int src0, int *done_dev, Counters *ctr,
+                                   int dbg, cudaStream_t st)
+{
+    constexpr int TX = 24, TY = 24, MINB = 3;
+    using TL = Tile4<TX, TY>;
+    if (tile_index() != 1 || !g.wrap_y) return cudaErrorNotSupported;
+    // a clipped last tile narrower than the margin would make the image producers span two tiles
+    const int remx = g.cps % TX, remy = g.rows % TY;
+    if ((remx && remx < kMX) || (remy && remy < kMY) || g.cps < 2 * TX || g.rows < 2 * TY) return cudaErrorNotSupported;
+    auto kern = sweep4_persistent<TX, TY, MINB>;
+    static int grid_max = 0;
+    if (!grid_max) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TL::THREADS, TL::SMEM);
+        if (e != cudaSuccess) return e;
+        if (!coop || per_sm < 1) return cudaErrorNotSupported;
+        grid_max = sms * per_sm;
+    }
+    if (n_steps > kStepCap) return cudaErrorInvalidValue;
+    const int gx = (g.cps + TX - 1) / TX, gy = (g.rows + TY - 1) / TY;
+    const int grid = gx * gy < grid_max ? gx * gy : grid_max;
+    static std::mutex mu;
+    static cudaEvent_t batch_done = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    cudaError_t e;
+    if (!batch_done) { e = cudaEventCreateWithFlags(&batch_done, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    else { e = cudaEventSynchronize(batch_done); if (e != cudaSuccess) return e; }     // c_steps is free again
+    e = cudaMemcpyToSymbolAsync(c_steps, steps_host, (size_t)n_steps * sizeof(StepArgs), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);                  // steps_host may be pageable and reused by the caller
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(done_dev, 0, (size_t)gx * gy * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    CUtensorMap t0 = *(const CUtensorMap *)tmap0, t1 = *(const CUtensorMap *)tmap1;
+    Geom4 gg = g;
+    void *args[] = { &t0, &t1, &buf0, &buf1, &gg, &n_steps, &src0, &done_dev, &ctr, &dbg };
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(TL::THREADS), args, TL::SMEM, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(batch_done, st);
+}
+
+int pmc4_tile_count(const Geom4 &g)
+{
+    const TileCfg c = kCfgs[tile_index()];
+    return ((g.cps + c.tx - 1) / c.tx) * ((g.rows + c.ty - 1) / c.ty);
+}
 
 int pmc4_tile_rows(const Geom4 &g) { const int ty = kCfgs[tile_index()].ty; return (g.rows + ty - 1) / ty; }
 
