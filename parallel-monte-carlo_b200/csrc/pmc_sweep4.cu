@@ -114,12 +114,16 @@ __device__ __forceinline__ float2 pair2(float qx0, float qx1, float qy0, float q
 template <int NS, int PLC>
 __device__ __forceinline__ float cell_min_d2(const float4 *cp, float npx, float npy)
 {
-    const float4 p0 = cp[0], p1 = cp[PLC], p2 = cp[2 * PLC];
+    const float4 p0 = cp[0], p1 = cp[PLC];
     const float2 nx = make_float2(npx, npx), ny = make_float2(npy, npy);
     const float2 a = pair2(p0.x, p0.y, p1.x, p1.y, nx, ny);
     const float2 b = pair2(p0.z, p0.w, p1.z, p1.w, nx, ny);
-    const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
-    float m = fminf(fminf(fminf(a.x, a.y), fminf(b.x, b.y)), fminf(c.x, c.y));
+    float m = fminf(fminf(a.x, a.y), fminf(b.x, b.y));
+    if (NS >= 6) {
+        const float4 p2 = cp[2 * PLC];
+        const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
+        m = fminf(m, fminf(c.x, c.y));
+    }
     if (NS == 8) {
         const float4 p3 = cp[3 * PLC];
         const float2 e = pair2(p3.x, p3.y, p3.z, p3.w, nx, ny);
@@ -267,13 +271,16 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
         float2 d01 = pair2(ox[0], ox[1], oy[0], oy[1], npx, npy);
         float2 d23 = pair2(ox[2], ox[3], oy[2], oy[3], npx, npy);
-        const float2 d45 = pair2(ox[4], ox[5], oy[4], oy[5], npx, npy);
         const float big = 3.0e38f;
         if (s == 0) d01.x = big;
         if (s == 1) { d01.y = cA ? big : d01.y; d01.x = cA ? d01.x : big; }
         if (s == 2) { d23.x = cA ? big : d23.x; d01.x = cA ? d01.x : big; }
         if (s == 3) { d23.y = cA ? big : d23.y; d01.y = cB ? big : d01.y; d01.x = (cA | cB) ? d01.x : big; }
-        m = fminf(m, fminf(fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)), fminf(d45.x, d45.y)));
+        m = fminf(m, fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)));
+        if (NS >= 6) {
+            const float2 d45 = pair2(ox[4], ox[5], oy[4], oy[5], npx, npy);
+            m = fminf(m, fminf(d45.x, d45.y));
+        }
         if (NS == 8) {
             const float2 d67 = pair2(ox[6], ox[7], oy[6], oy[7], npx, npy);
             m = fminf(m, fminf(d67.x, d67.y));
@@ -292,7 +299,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     // cpy_D_sh_to_Disk subsweep.h:29-36 (shuffled order is written back, like the reference)
     pown[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
     pown[PLC] = make_float4(oy[0], oy[1], oy[2], oy[3]);
-    pown[2 * PLC] = make_float4(ox[4], ox[5], oy[4], oy[5]);
+    if (NS >= 6) pown[2 * PLC] = make_float4(ox[4], ox[5], oy[4], oy[5]);
     if (NS == 8) pown[3 * PLC] = make_float4(ox[6], ox[7], oy[6], oy[7]);
 }
 
@@ -336,7 +343,9 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const S
             c.x47 = make_float4(p2.x, p2.y, p3.x, p3.y); c.y47 = make_float4(p2.z, p2.w, p3.z, p3.w);
             c.cnt = decode_cnt8(p3);
         } else {
-            c.x47 = make_float4(p2.x, p2.y, kSent, kSent); c.y47 = make_float4(p2.z, p2.w, 0.f, 0.f);
+            // NS = 6 / 4: the higher slots are known to be unused in this tile
+            c.x47 = NS == 6 ? make_float4(p2.x, p2.y, kSent, kSent) : make_float4(kSent, kSent, kSent, kSent);
+            c.y47 = NS == 6 ? make_float4(p2.z, p2.w, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
             c.cnt = decode_cnt6(p2);
         }
     };
@@ -427,19 +436,31 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
     __syncthreads();
     mbar_wait(mbar, phase);
 
-    // does any staged cell hold 7 or 8 disks (x6 in use)?  Otherwise P3 is never needed.
+    // does any staged cell hold 7 or 8 disks (x6 in use), or 5 or 6 (x4 in use)?  Otherwise P3
+    // (P3 and P2) are never needed: bit 1 / bit 0 of `big`
     int big = 0;
     {
+        const float *x4 = reinterpret_cast<const float *>(sm + 2 * PLC);
         const float *x6 = reinterpret_cast<const float *>(sm + 3 * PLC);
 #pragma unroll 1
-        for (int c = tid; c < TL::PLB; c += THREADS) big |= x6[c * 4] < kSentTest;
+        for (int c = tid; c < TL::PLB; c += THREADS)
+            big |= (x6[c * 4] < kSentTest ? 2 : 0) | (x4[c * 4] < kSentTest ? 1 : 0);
     }
-    const bool ns8 = __syncthreads_or(big) || (a.dbg_skip & 8);
+    big = __syncthreads_or(big & 2) ? 2 : (__syncthreads_or(big & 1) ? 1 : 0);
+    if (a.dbg_skip & 8) big = 2;
+    if ((a.dbg_skip & 16) && big == 0) big = 1;
+    const bool ns8 = big == 2, ns4 = big == 0;
 
     // ------------------------------------------------------------ the four sub-sweeps
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
     if (!(a.dbg_skip & 1)) {
-        if (!ns8) {
+        if (ns4) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                colour_pass<4, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                __syncthreads();
+            }
+        } else if (!ns8) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
                 colour_pass<6, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
@@ -456,7 +477,8 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
 
     // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
     if (do_shift) {
-        if (!ns8) shift_pass<6, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
+        if (ns4) shift_pass<4, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
+        else if (!ns8) shift_pass<6, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
         else shift_pass<8, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
     }
 
@@ -741,11 +763,13 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const 
 {
     using TL = Tile4<TX, TY>;
     auto kern = sweep4_kernel<TX, TY, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = { false };           // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int gy = (g.rows + TY - 1) / TY;
     SweepArgs a = a_in;
