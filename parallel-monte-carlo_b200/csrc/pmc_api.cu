@@ -214,6 +214,7 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
         pmc4_alloc_shape(g.cps, g.rows, &q.CH, &q.ROWS);
         q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale;
         q.seed_lo = g.seed_lo; q.seed_hi = g.seed_hi;
+        q.try_ns4 = (double)p.n_particles / ((double)g.cps * (double)g.cps) < 2.5;   // a performance hint only
         for (int r = 0; r < 10; r++) { q.pk0[r] = g.seed_lo + (unsigned)r * 0x9E3779B9u; q.pk1[r] = g.seed_hi + (unsigned)r * 0xBB67AE85u; }
         h->v4_ok = (p.n_M == 4) && ((double)g.w >= 2.0 * (double)p.sigma_d * (1.0 + 1e-5)) && g.cps >= 48 &&
                    g.rows >= 2 * kMY && (p.n_ranks == 1 || kGhostRows == kMY);

@@ -77,6 +77,7 @@ struct Geom4 {
     int ROWS;                   // allocated rows
     float w, hw, sigma2, dscale;
     unsigned seed_lo, seed_hi;
+    int try_ns4;                // mean occupancy is low: worth scanning for tiles whose cells all hold <= 4 disks
     unsigned pk0[10], pk1[10];  // Philox round keys seed + r * (0x9E3779B9, 0xBB67AE85): constant-bank operands
 };
 int pmc4_tile_x();

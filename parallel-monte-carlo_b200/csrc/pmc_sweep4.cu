@@ -442,9 +442,14 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
     {
         const float *x4 = reinterpret_cast<const float *>(sm + 2 * PLC);
         const float *x6 = reinterpret_cast<const float *>(sm + 3 * PLC);
+        if (g.try_ns4) {
 #pragma unroll 1
-        for (int c = tid; c < TL::PLB; c += THREADS)
-            big |= (x6[c * 4] < kSentTest ? 2 : 0) | (x4[c * 4] < kSentTest ? 1 : 0);
+            for (int c = tid; c < TL::PLB; c += THREADS)
+                big |= (x6[c * 4] < kSentTest ? 2 : 0) | (x4[c * 4] < kSentTest ? 1 : 0);
+        } else {            // dense system: no tile will qualify for NS = 4, scan one plane only
+#pragma unroll 1
+            for (int c = tid; c < TL::PLB; c += THREADS) big |= x6[c * 4] < kSentTest ? 2 : 1;
+        }
     }
     big = __syncthreads_or(big & 2) ? 2 : (__syncthreads_or(big & 1) ? 1 : 0);
     if (a.dbg_skip & 8) big = 2;
