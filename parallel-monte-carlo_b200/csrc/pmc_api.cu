@@ -459,7 +459,8 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     // EXPERIMENTAL, off by default: measured 0.48 ms / sweep against 0.34 ms for one launch per sweep at
     // N = 2^24; kept selectable for the round-2 investigation
     static const int persistent = [] { const char *e = getenv("PMC_PERSISTENT"); return e ? atoi(e) : 0; }();
-    const int kBatch = pmc4_step_capacity();
+    static const int pbatch = [] { const char *e = getenv("PMC_PBATCH"); return e ? atoi(e) : 0; }();
+    const int kBatch = (pbatch > 0 && pbatch < pmc4_step_capacity()) ? pbatch : pmc4_step_capacity();
     if (persistent && h->p.n_ranks == 1) {
         // single GPU: batches of sweeps in ONE cooperative launch each (no per-sweep launch, no idle tail)
         if (!h->done_dev) CK(cudaMalloc(&h->done_dev, (size_t)pmc4_tile_count(h->g4) * sizeof(int)));

@@ -648,8 +648,9 @@ sweep4_persistent(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             process_tile<TX, TY, false>(src ? &tm1 : &tm0, src ? buf0 : buf1, g, sa, ctr, tbx, tby, sm, mbar, phase, my_trials, my_acc);
             flush_counters(ctr, my_trials, my_acc);
             phase ^= 1u;
-            __threadfence();            // this tile's stores are visible device-wide ...
-            __syncthreads();            // ... before thread 0 publishes it (also: smem is free for the next box)
+            // bar.sync orders every thread's stores before thread 0's release (cumulative at gpu scope);
+            // it also frees the shared memory for the next box
+            __syncthreads();
             if (tid == 0) st_release(done + tile, s + 1);
         }
     }

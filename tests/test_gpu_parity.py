@@ -383,3 +383,18 @@ def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
     c = mc.counters()
     assert (c["trials"], c["accepted"], c["lost"]) == (o.trials.value, o.accepted.value, o.lost)
     assert c["lost"] > 0 and c["status"] & 1
+
+
+def test_experimental_persistent_kernel_is_bit_exact():
+    """PMC_PERSISTENT=1 (off by default): many sweeps in one cooperative launch
+    with per-tile completion flags instead of kernel boundaries.  The switch is read once per
+    process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PMC_PERSISTENT="1", PMC_S="7", PMC_N=str(2 ** 16))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "debug_v4.py")], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "count mismatches 0" in out.stdout and "position mismatches 0" in out.stdout, out.stdout[-1500:]
