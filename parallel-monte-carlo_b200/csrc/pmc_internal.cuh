@@ -48,7 +48,8 @@ struct SweepArgs {
     int by_off;             // fused fast path: first tile row of this launch (boundary / interior split of slab runs)
     int by_n1, by_off2;     // grid rows >= by_n1 map to tile rows by_off2 + (row - by_n1) (second band)
     int prefetch_ahead;     // fused fast path: L2-prefetch the tile of block id + this (0 = off)
-    int dbg_skip;           // profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store
+    int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
+                            // 8 force the 8-slot instantiation, 16 never use the 4-slot one
 };
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`)

@@ -16,7 +16,9 @@
 //     so a tile never wraps.
 //   * cells hold <= 6 disks in all but ~1e-5 of the cases at phi = 0.70, w = 2 sigma: a tile
 //     whose staged cells all hold <= 6 runs the NS = 6 instantiation, which never touches P3
-//     (3 instead of 4 chunks per neighbour cell, 24 instead of 32 pair tests per trial).
+//     (3 instead of 4 chunks per neighbour cell, 24 instead of 32 pair tests per trial); a
+//     tile whose cells all hold <= 4 (dilute systems) runs NS = 4 and touches neither P3 nor
+//     P2; NS = 8 covers the rest.  The choice is per tile, from a scan of the staged box.
 //   * the cell count lives in-band: unused slots have x = sentinel; a cell with fewer than 8
 //     (6) disks carries its count in the bits of y7 (y5).  No count array on the hot path.
 //   * the grid shift of THIS sweep is applied while the tile leaves shared memory (the tile
