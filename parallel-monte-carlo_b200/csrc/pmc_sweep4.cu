@@ -117,19 +117,25 @@ template <int NS, int PLC>
 __device__ __forceinline__ float cell_min_d2(const float4 *cp, float npx, float npy)
 {
     const float4 p0 = cp[0], p1 = cp[PLC];
+    // sign bit of y3 = "this cell holds 5 or more disks" (cell-local coordinates are positive):
+    // only then are P2 (and P3) fetched, so quarter-warps whose 8 neighbour cells all hold <= 4
+    // disks (61 % of them at phi = 0.70) spend no shared-memory wavefront on those planes
+    const bool more = NS >= 6 && __float_as_int(p1.w) < 0;
     const float2 nx = make_float2(npx, npx), ny = make_float2(npy, npy);
     const float2 a = pair2(p0.x, p0.y, p1.x, p1.y, nx, ny);
-    const float2 b = pair2(p0.z, p0.w, p1.z, p1.w, nx, ny);
+    const float2 b = pair2(p0.z, p0.w, p1.z, fabsf(p1.w), nx, ny);
     float m = fminf(fminf(a.x, a.y), fminf(b.x, b.y));
     if (NS >= 6) {
-        const float4 p2 = cp[2 * PLC];
-        const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
-        m = fminf(m, fminf(c.x, c.y));
-    }
-    if (NS == 8) {
-        const float4 p3 = cp[3 * PLC];
-        const float2 e = pair2(p3.x, p3.y, p3.z, p3.w, nx, ny);
-        m = fminf(m, fminf(e.x, e.y));
+        if (more) {
+            const float4 p2 = cp[2 * PLC];
+            const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
+            m = fminf(m, fminf(c.x, c.y));
+            if (NS == 8) {
+                const float4 p3 = cp[3 * PLC];
+                const float2 e = pair2(p3.x, p3.y, p3.z, p3.w, nx, ny);
+                m = fminf(m, fminf(e.x, e.y));
+            }
+        }
     }
     return m;
 }
@@ -238,7 +244,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     };
 
     float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
-    float oy[8] = { p1.x, p1.y, p1.z, p1.w, p2.z, p2.w, p3.z, p3.w };
+    float oy[8] = { p1.x, p1.y, p1.z, fabsf(p1.w), p2.z, p2.w, p3.z, p3.w };     // y3 carries the "5 or more" flag in its sign
     uint32_t rw[8];
     philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.pk0, g.pk1, rw[0], rw[1], rw[2], rw[3]);
     philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.pk0, g.pk1, rw[4], rw[5], rw[6], rw[7]);
@@ -300,7 +306,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     }
     // cpy_D_sh_to_Disk subsweep.h:29-36 (shuffled order is written back, like the reference)
     pown[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
-    pown[PLC] = make_float4(oy[0], oy[1], oy[2], oy[3]);
+    pown[PLC] = make_float4(oy[0], oy[1], oy[2], cnt >= 5 ? -oy[3] : oy[3]);
     if (NS >= 6) pown[2 * PLC] = make_float4(ox[4], ox[5], oy[4], oy[5]);
     if (NS == 8) pown[3 * PLC] = make_float4(ox[6], ox[7], oy[6], oy[7]);
 }
@@ -339,7 +345,7 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const S
     auto load_cell = [&](int i, int j, CellRegs &c) {           // P0..P3 -> plain x / y registers
         const float4 *p = cell_ptr(i, j);
         const float4 p0 = p[0], p1 = p[PLC], p2 = p[2 * PLC];
-        c.x03 = p0; c.y03 = p1;
+        c.x03 = p0; c.y03 = make_float4(p1.x, p1.y, p1.z, fabsf(p1.w));
         if (NS == 8) {
             const float4 p3 = p[3 * PLC];
             c.x47 = make_float4(p2.x, p2.y, p3.x, p3.y); c.y47 = make_float4(p2.z, p2.w, p3.z, p3.w);
@@ -378,6 +384,7 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const S
             // in-band counts (plain order: y5 = plane 3 word 1, y7 = plane 3 word 3)
             if (nNew < PMC_NMAX) fx[3 * PLC * 4 + 3] = __int_as_float(nNew);
             if (nNew < 6) fx[3 * PLC * 4 + 1] = __int_as_float(nNew);
+            if (nNew >= 5) fx[2 * PLC * 4 + 3] = -fx[2 * PLC * 4 + 3];      // "5 or more" flag: sign of y3
             if (dropped) {
                 atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
                 if ((unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy)
@@ -697,6 +704,7 @@ __global__ void import4_kernel(const float *__restrict__ disk, const int16_t *__
         } else if (pl == 1) {
 #pragma unroll
             for (int q = 0; q < 4; q++) if (q < cnt) v[q] = __ldg(c + 8 + q);
+            if (cnt >= 5) v[3] = -v[3];                 // "5 or more" flag: sign of y3
         } else {
 #pragma unroll
             for (int q = 0; q < 2; q++)
@@ -727,7 +735,7 @@ __global__ void export4_kernel(const float4 *__restrict__ in, float4 *__restrict
     float4 v;
     int s0;
     if (ch == 0) { v = __ldg(cp); s0 = 0; }
-    else if (ch == 2) { v = __ldg(cp + ps); s0 = 0; }
+    else if (ch == 2) { v = __ldg(cp + ps); v.w = fabsf(v.w); s0 = 0; }
     else {
         const float4 p2 = __ldg(cp + 2 * ps);
         v = ch == 1 ? make_float4(p2.x, p2.y, p3.x, p3.y) : make_float4(p2.z, p2.w, p3.z, p3.w);
