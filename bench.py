@@ -35,9 +35,9 @@ N_M, NMAX, SIGMA, CELL_W, SEED = 4, 8, 1.0, 2.0, 1234
 METRIC = "hard-disk trial moves/sec"
 UNIT = "moves/s"
 
-# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_summary.txt):
+# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_v6_summary.txt):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 308.9e6 + 257.5e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 308.9e6 + 258.1e6}
 
 
 def algorithmic_bytes_per_sweep(n_particles, n_cells):
