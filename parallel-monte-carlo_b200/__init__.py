@@ -18,7 +18,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libpmc_b200.so")
+LIB_PATH = os.environ.get("PMC_LIB_PATH") or os.path.join(_HERE, "libpmc_b200.so")     # the override is a development aid
 SOURCES = ["pmc_api.cu", "pmc_cells.cu", "pmc_sweep.cu", "pmc_sweep4.cu"]
 HEADERS = ["pmc_internal.cuh", os.path.join("..", "..", "include", "pmc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

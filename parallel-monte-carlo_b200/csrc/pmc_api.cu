@@ -92,10 +92,11 @@ struct pmc_handle {
     // slab runs: ghost rows travel on a side stream while the interior tile rows are computed
     cudaStream_t comm_stream;
     cudaEvent_t ev_boundary, ev_exchanged;
-    // persistent multi-sweep kernel: per-sweep arguments and per-tile completion flags
-    int *done_dev;
+    // crowded-cell flags of the two internal buffers (one word per 8 x 8 cells, epoch-stamped)
+    unsigned *v4_flags[2];
+    unsigned v4_epoch[2], v4_epoch_next;
     long long launches;         // kernels launched by this handle since the last pmc_reset_counters
-    alignas(64) unsigned char v4_tmap[2][128];
+    alignas(64) unsigned char v4_tmap[2][2][128];   // [buffer][0: full-tile box, 1: half-height box]
 };
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
@@ -211,7 +212,7 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
         // far above float rounding; tiny boxes would need more than one periodic image
         Geom4 &q = h->g4;
         q.cps = g.cps; q.row0 = g.row0; q.rows = g.rows; q.wrap_y = g.wrap_y;
-        pmc4_alloc_shape(g.cps, g.rows, &q.CH, &q.ROWS);
+        pmc4_alloc_shape(g.cps, g.rows, &q.CH, &q.ROWS, &q.FW, &q.FH);
         q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale;
         q.seed_lo = g.seed_lo; q.seed_hi = g.seed_hi;
         q.try_ns4 = (double)p.n_particles / ((double)g.cps * (double)g.cps) < 2.5;   // a performance hint only
@@ -253,7 +254,7 @@ int pmc_destroy(pmc_handle *h)
     cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
     cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
     cudaFree(h->v4_buf[0]); cudaFree(h->v4_buf[1]);
-    cudaFree(h->done_dev);
+    cudaFree(h->v4_flags[0]); cudaFree(h->v4_flags[1]);
     if (h->ktime_pending) {
         for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         delete h->ktime_pending;
@@ -427,22 +428,39 @@ static int v4_exchange_async(pmc_handle *h, float4 *buf, cudaStream_t st)
 // (4 colours + this sweep's shiftCells applied while the tile is stored), -> caller layout.
 static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n_sweeps)
 {
+    const size_t flag_bytes = (size_t)h->g4.FW * h->g4.FH * sizeof(unsigned);
     for (int b = 0; b < 2; b++)
         if (!h->v4_buf[b]) {
             CK(cudaMalloc(&h->v4_buf[b], v4_bytes(h)));
-            int rc = pmc4_make_tensor_map(h->v4_tmap[b], h->v4_buf[b], h->g4);
-            if (rc) return rc;
+            CK(cudaMalloc(&h->v4_flags[b], flag_bytes));
+            CK(cudaMemsetAsync(h->v4_flags[b], 0, flag_bytes, h->stream));
+            for (int half = 0; half < 2; half++) {
+                int rc = pmc4_make_tensor_map(h->v4_tmap[b][half], h->v4_buf[b], h->g4, half);
+                if (rc) return rc;
+            }
             h->v4_padded = 0;
+            h->v4_epoch_next = 1;                   // 0 = "never flagged" (the memset above)
         }
+    auto next_epoch = [&]() -> unsigned {
+        if (h->v4_epoch_next == 0xFFFFFFFFu) {      // wrap: forget every stamp (once per 4e9 sweeps)
+            cudaMemsetAsync(h->v4_flags[0], 0, flag_bytes, h->stream);
+            cudaMemsetAsync(h->v4_flags[1], 0, flag_bytes, h->stream);
+            h->v4_epoch_next = 1;
+        }
+        return h->v4_epoch_next++;
+    };
     const int ghost = h->g.ghost;
-    CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[0], h->stream)); h->launches += 1;
+    h->v4_epoch[0] = next_epoch();
+    CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[0], h->v4_flags[0], h->v4_epoch[0], h->stream)); h->launches += 1;
     if (!h->v4_padded) {        // cells beyond the margins are never written again: make them valid once
-        CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[1], h->stream)); h->launches += 1;
+        h->v4_epoch[1] = next_epoch();
+        CK(pmc4_launch_import(h->g4, ghost, (const float4 *)d_disk, d_n, h->v4_buf[1], h->v4_flags[1], h->v4_epoch[1], h->stream)); h->launches += 1;
         h->v4_padded = 1;
     }
     int cur = 0;
     static const int dbg = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
     static const int overlap = [] { const char *e = getenv("PMC_OVERLAP"); return e ? atoi(e) : 1; }();
+    static const int fast_ok = [] { const char *e = getenv("PMC_FAST"); return e ? atoi(e) : 1; }();
     if (h->p.n_ranks > 1 && !h->comm_stream) {
         int prio_lo = 0, prio_hi = 0;               // the exchange must not queue behind the interior tiles
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -455,43 +473,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     CK(cudaEventCreate(&k0));
     CK(cudaEventCreate(&k1));
     CK(cudaEventRecord(k0, h->stream));
-    int t_done = 0;
-    // EXPERIMENTAL, off by default: measured 0.48 ms / sweep against 0.34 ms for one launch per sweep at
-    // N = 2^24; kept selectable for the round-2 investigation
-    static const int persistent = [] { const char *e = getenv("PMC_PERSISTENT"); return e ? atoi(e) : 0; }();
-    static const int pbatch = [] { const char *e = getenv("PMC_PBATCH"); return e ? atoi(e) : 0; }();
-    const int kBatch = (pbatch > 0 && pbatch < pmc4_step_capacity()) ? pbatch : pmc4_step_capacity();
-    if (persistent && h->p.n_ranks == 1) {
-        // single GPU: batches of sweeps in ONE cooperative launch each (no per-sweep launch, no idle tail)
-        if (!h->done_dev) CK(cudaMalloc(&h->done_dev, (size_t)pmc4_tile_count(h->g4) * sizeof(int)));
-        std::vector<Pmc4Step> steps;
-        while (t_done < n_sweeps) {
-            const int nb = n_sweeps - t_done < kBatch ? n_sweeps - t_done : kBatch;
-            steps.resize(nb);
-            for (int k = 0; k < nb; k++) {
-                const uint64_t sweep = sweep0 + (uint64_t)(t_done + k);
-                int order[4], f;
-                float d;
-                pmc_schedule(h, sweep, order, &f, &d);
-                unsigned mask = 0;
-                for (int c = 0; c < 4; c++) {
-                    int off[2];
-                    pmc_colour_to_off(order[c], off);
-                    mask |= ((unsigned)off[0] | ((unsigned)off[1] << 1)) << (2 * c);
-                }
-                steps[k].offmask = mask; steps[k].sweep_lo = (unsigned)sweep; steps[k].sweep_hi = (unsigned)(sweep >> 32);
-                steps[k].shift_f = f; steps[k].shift_d = d;
-            }
-            cudaError_t pe = pmc4_launch_persistent(h->g4, h->v4_tmap[0], h->v4_tmap[1], h->v4_buf[0], h->v4_buf[1],
-                                                    steps.data(), nb, cur, h->done_dev, h->d_ctr, dbg, h->stream);
-            if (pe == cudaErrorNotSupported) { cudaGetLastError(); break; }
-            CK(pe);
-            h->launches += 2;                           // flag memset + the cooperative kernel
-            cur ^= (nb & 1);
-            t_done += nb;
-        }
-    }
-    for (int t = t_done; t < n_sweeps; t++) {
+    for (int t = 0; t < n_sweeps; t++) {
         const uint64_t sweep = sweep0 + (uint64_t)t;
         int order[4], f;
         float d;
@@ -508,22 +490,28 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         a.shift_on = 1; a.shift_f = f; a.shift_d = d;
         a.dbg_skip = dbg;
         a.prefetch_ahead = pf_ahead;
+        h->v4_epoch[cur ^ 1] = next_epoch();
+        a.flag_in = h->v4_flags[cur]; a.epoch_in = h->v4_epoch[cur];
+        a.flag_out = h->v4_flags[cur ^ 1]; a.epoch_out = h->v4_epoch[cur ^ 1];
+        const void *tm = h->v4_tmap[cur][0], *tmh = h->v4_tmap[cur][1];
+        float4 *dst = h->v4_buf[cur ^ 1];
         const int gy = pmc4_tile_rows(h->g4), ty = pmc4_tile_y();
         // tile rows that hold one of the kMY owned rows next to a slab face
         const int top0 = (h->g4.rows - kMY) / ty;
         if (h->p.n_ranks > 1 && overlap && top0 > 1 && top0 < gy) {
-            // boundary tile rows first; their ghost-row exchange overlaps the interior rows
-            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 0, 1, top0, gy - top0)); h->launches += 1;
+            // boundary tile rows first (their boxes hold ghost rows, which carry no crowded-cell flags: the
+            // 4-plane kernel); their ghost-row exchange overlaps the interior rows (the fast kernel)
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, 0, 0, 1, top0, gy - top0)); h->launches += 1;
             CK(cudaEventRecord(h->ev_boundary, h->stream));
-            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream, 1, top0 - 1)); h->launches += 1;
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok, 1, top0 - 1)); h->launches += 1;
             CK(cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
-            int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1], h->comm_stream);
+            int rc = v4_exchange_async(h, dst, h->comm_stream);
             if (rc) return rc;
             CK(cudaEventRecord(h->ev_exchanged, h->comm_stream));
             CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged, 0));
         } else {
-            CK(pmc4_launch_sweep(h->g4, h->v4_tmap[cur], h->v4_buf[cur ^ 1], a, h->d_ctr, h->stream)); h->launches += 1;
-            int rc = v4_exchange_async(h, h->v4_buf[cur ^ 1], h->stream);
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, h->p.n_ranks == 1 ? fast_ok : 0)); h->launches += 1;
+            int rc = v4_exchange_async(h, dst, h->stream);
             if (rc) return rc;
         }
         cur ^= 1;

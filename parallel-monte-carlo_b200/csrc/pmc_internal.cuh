@@ -48,8 +48,13 @@ struct SweepArgs {
     int by_off;             // fused fast path: first tile row of this launch (boundary / interior split of slab runs)
     int by_n1, by_off2;     // grid rows >= by_n1 map to tile rows by_off2 + (row - by_n1) (second band)
     int prefetch_ahead;     // fused fast path: L2-prefetch the tile of block id + this (0 = off)
+    // fused fast path: crowded-cell flags (one word per 8 x 8 block of internal cells, stamped with the
+    // epoch of the sweep that stored a cell with 7 or 8 disks there; never cleared)
+    const unsigned *flag_in;    // flags of the state being read, valid where == epoch_in
+    unsigned *flag_out;         // flags of the state being written, stamped with epoch_out
+    unsigned epoch_in, epoch_out;
     int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
-                            // 8 force the 8-slot instantiation, 16 never use the 4-slot one
+                            // 8 treat every tile as crowded, 16 never use the 4-slot instantiation
 };
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`)
@@ -76,6 +81,7 @@ struct Geom4 {
     int cps, row0, rows, wrap_y;
     int CH;                     // float4 chunks per (row, plane, parity) run
     int ROWS;                   // allocated rows
+    int FW, FH;                 // crowded-cell flag grid: words per row, rows
     float w, hw, sigma2, dscale;
     unsigned seed_lo, seed_hi;
     int try_ns4;                // mean occupancy is low: worth scanning for tiles whose cells all hold <= 4 disks
@@ -83,21 +89,17 @@ struct Geom4 {
 };
 int pmc4_tile_x();
 int pmc4_tile_y();
-void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS);
-int pmc4_make_tensor_map(void *tmap_out128, const float4 *base, const Geom4 &g);
-cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out, cudaStream_t st);
+void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS, int *FW, int *FH);
+int pmc4_make_tensor_map(void *tmap_out128, const float4 *base, const Geom4 &g, int half);
+cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out,
+                               unsigned *flags, unsigned epoch, cudaStream_t st);
 cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, float4 *disk, int16_t *n, cudaStream_t st);
-// tile rows [by0, by0 + nby) of one sweep (nby <= 0: all rows)
-// optional second band [by1, by1 + nby1) in the same launch
-cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
-                              Counters *ctr, cudaStream_t st, int by0 = 0, int nby = 0, int by1 = 0, int nby1 = 0);
+// tile rows [by0, by0 + nby) of one sweep (nby <= 0: all rows), optional second band [by1, by1 + nby1)
+// in the same launch; fast = 1: the 3-plane / 4-CTA kernel (boxes must not touch slab ghost rows)
+cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a,
+                              Counters *ctr, cudaStream_t st, int fast, int by0 = 0, int nby = 0, int by1 = 0, int nby1 = 0);
 int pmc4_tile_rows(const Geom4 &g);
 int pmc4_tile_count(const Geom4 &g);
-struct Pmc4Step { unsigned offmask, sweep_lo, sweep_hi; int shift_f; float shift_d; };   // = StepArgs of pmc_sweep4.cu
-int pmc4_step_capacity();
-cudaError_t pmc4_launch_persistent(const Geom4 &g, const void *tmap0, const void *tmap1, float4 *buf0, float4 *buf1,
-                                   const void *steps_host, int n_steps, int src0, int *done_dev, Counters *ctr,
-                                   int dbg, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ Philox4x32-10

@@ -14,11 +14,15 @@
 //     The box is surrounded by margins (kMX columns, kMY rows) holding periodic images, written
 //     by the CTA that produces the original cell (single GPU) or by the NCCL ring (slab rows),
 //     so a tile never wraps.
-//   * cells hold <= 6 disks in all but ~1e-5 of the cases at phi = 0.70, w = 2 sigma: a tile
-//     whose staged cells all hold <= 6 runs the NS = 6 instantiation, which never touches P3
-//     (3 instead of 4 chunks per neighbour cell, 24 instead of 32 pair tests per trial); a
-//     tile whose cells all hold <= 4 (dilute systems) runs NS = 4 and touches neither P3 nor
-//     P2; NS = 8 covers the rest.  The choice is per tile, from a scan of the staged box.
+//   * cells hold <= 6 disks in all but ~1e-5 of the cases at phi = 0.70, w = 2 sigma.  Every
+//     store records, per block of 8 x 8 internal cells, whether it wrote a cell with 7 or 8
+//     disks (an epoch-stamped flag word, so nothing is ever cleared).  A tile whose staged box
+//     touches no flagged block takes the FAST path: plane P3 is not even staged (3 TMA boxes,
+//     56 KB of shared memory, 64 registers: FOUR CTAs per SM instead of three) and the NS = 6
+//     instantiation runs (3 instead of 4 chunks per neighbour cell, 24 instead of 32 pair
+//     tests per trial); if all staged cells hold <= 4 (dilute systems) NS = 4 runs and P2 is
+//     not touched either.  A flagged tile is processed by the same CTA as two half-height
+//     tiles with all four planes (they fit the same 56 KB) and NS chosen from a scan.
 //   * the cell count lives in-band: unused slots have x = sentinel; a cell with fewer than 8
 //     (6) disks carries its count in the bits of y7 (y5).  No count array on the hot path.
 //   * the grid shift of THIS sweep is applied while the tile leaves shared memory (the tile
@@ -30,12 +34,13 @@
 #include "pmc_internal.cuh"
 #include <cuda.h>      // CUtensorMap type only; the encoder comes from cudaGetDriverEntryPoint
 #include <stdlib.h>
-#include <mutex>
 
 namespace {
 
 constexpr float kSent = PMC_SENTINEL;
 constexpr float kSentTest = 1.0e17f;      // x < kSentTest <=> slot in use
+constexpr int kNT = 256;                  // threads per CTA of every kernel in this file
+constexpr int kFB = 3;                    // log2 of the flag block edge (8 x 8 internal cells per flag word)
 
 template <int TX, int TY>
 struct Tile4 {
@@ -49,9 +54,11 @@ struct Tile4 {
     // TX = 24 always fits; TX = 26 fits when the tile carries no extra column (shift along y).
     static constexpr int NAX = 16, NAY = (TY + 2 * H) / 2;
     static constexpr int THREADS = NAX * NAY;
-    static constexpr size_t SMEM = (size_t)4 * PLC * 16 + 16;
+    static constexpr size_t PLANE_BYTES = (size_t)PLC * 16;
     static_assert(TX % 2 == 0 && TY % 2 == 0 && TX + 2 * H <= 2 * NAX + 2, "tile shape");
     static_assert(4 * HB <= 256 && SYB <= 256, "TMA box extents");
+    static_assert(THREADS <= kNT, "one thread per active cell of a colour");
+    static_assert(PLC > PLB, "the mbarrier lives in the padding behind plane 0");
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -148,18 +155,26 @@ __device__ __forceinline__ float signed_odd24(uint32_t r)
     return __uint_as_float(__float_as_uint(mag) | (r & 0x80000000u));
 }
 
-// V2 shiftCells.h:23-112 for one destination cell.  The result is written in place into the
-// staged tile in the PLAIN plane order (x0-3 | x4-7 | y0-3 | y4-7: slot -> address is one
-// shift and one multiply-add); the store phase converts to P0..P3 on the way out.
-// fx points at the first float of the destination cell's first chunk.
-template <int NS, int F, int PLC>
-__device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRegs &up, float d, float w,
-                                               float sshift, float *fx, int *dropped)
+// V2 shiftCells.h:23-112 for one destination cell.  The result is scattered in place into the
+// staged tile in PAIR order: chunk c of the cell (plane c) = (x_2c, y_2c, x_2c+1, y_2c+1), so
+// that one 8-byte store places a disk and the slot -> address walk is two adds (+8, then
+// +plane stride - 8, alternating); the store phase converts to P0..P3 on the way out.
+// NPL = 3 (fast path, P3 not staged): slots 6 and 7 do not exist in shared memory; the rare
+// immigrants that land there are returned in `ext` (P3 layout) and go straight to HBM.
+// cb points at the first byte of the destination cell's first chunk.
+__device__ __forceinline__ void sts_pair(unsigned saddr, float x, float y)
 {
-    constexpr int PF = PLC * 4;                         // floats between consecutive planes
-    float *pf = F == 0 ? fx : fx + 2 * PF;              // f-coordinate plane (slots 0-3)
-    constexpr int OFF = F == 0 ? 2 * PF : -2 * PF;      // to the other coordinate
-    int n = 0, drop = 0;
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(x), "f"(y) : "memory");
+}
+
+// returns the number of disks that WANT to be in the cell (more than 2 * NPL: the caller takes the rare path)
+template <int NS, int F, int NPL, int PLC>
+__device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRegs &up, float d, float w,
+                                               float sshift, unsigned scell, unsigned sdump, int &n_own)
+{
+    constexpr unsigned PS = PLC * 16;
+    unsigned sa = scell, step = 8;                      // next free slot; the walk alternates +8 / +PS-8
+    const unsigned lim = scell + NPL * PS;
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         const float fc = F == 0 ? f4get(own.x03, own.x47, i) : f4get(own.y03, own.y47, i);
@@ -167,26 +182,75 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
         const float D = __fadd_rn(fc, -d);
         // unused x slots hold the sentinel and fail on their own; unused y slots hold 0 / the count
         if ((F == 0 || i < own.cnt) && D > 0.0f && D <= w) {    // shiftCells.h:62
-            float *p = pf + n + (n >> 2) * (PF - 4);
-            p[0] = D; p[OFF] = oc;
-            n++;
+            sts_pair(sa, F == 0 ? D : oc, F == 0 ? oc : D);
+            sa += step; step = PS - step;
         }
     }
+    n_own = (int)(sa - scell);                          // decoded by the rare path only
+    // immigrants: the walk goes on past the last staged plane (those stores land on a dump word),
+    // so the final position counts every disk, placed or not
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         const float fc = F == 0 ? f4get(up.x03, up.x47, i) : f4get(up.y03, up.y47, i);
         const float oc = F == 0 ? f4get(up.y03, up.y47, i) : f4get(up.x03, up.x47, i);
         const float D = __fadd_rn(fc, -d);
-        if (i < up.cnt && !(D > 0.0f && D <= w)) {      // shiftCells.h:94
-            if (n < PMC_NMAX) {
-                float *p = pf + n + (n >> 2) * (PF - 4);
-                p[0] = __fadd_rn(D, sshift); p[OFF] = oc;   // shiftCells.h:97
-                n++;
-            } else drop++;
+        if (i < up.cnt && !(D > 0.0f && D <= w)) {              // shiftCells.h:94
+            const float Ds = __fadd_rn(D, sshift);              // shiftCells.h:97
+            sts_pair(sa < lim ? sa : sdump, F == 0 ? Ds : oc, F == 0 ? oc : Ds);
+            sa += step; step = PS - step;
         }
     }
-    *dropped = drop;
-    return n;
+    const unsigned off = sa - scell;
+    return 2 * (int)(off / PS) + (step != 8u ? 1 : 0);
+}
+
+// a cell with 7 or 8 disks was produced (rare): stamp the flag word of its 8 x 8 block - and of
+// the blocks of its periodic images - so that the next sweep stages P3 for the tiles that see it;
+// on the fast path (P3 not in shared memory) also write its P3 chunk, images included
+__device__ __noinline__ void crowded_cell_out(float4 *dout, unsigned *flag_out, unsigned epoch, int cps, int rows,
+                                              int wrap_y, int CH, int FW, int X, int Y, int write_p3, float4 p3)
+{
+    const int ux = X - kMX, uy = Y - kMY;
+    const int ximg = ux < kMX ? cps : (ux >= cps - kMX ? -cps : 0);
+    const int yimg = wrap_y ? (uy < kMY ? rows : (uy >= rows - kMY ? -rows : 0)) : 0;
+    for (int q = 0; q < 4; q++) {
+        if (((q & 1) && !ximg) || ((q & 2) && !yimg)) continue;
+        const int XX = X + ((q & 1) ? ximg : 0), YY = Y + ((q & 2) ? yimg : 0);
+        flag_out[(YY >> kFB) * FW + (XX >> kFB)] = epoch;
+        if (write_p3) dout[((long long)(YY * 4 + 3) * 2 + (XX & 1)) * CH + (XX >> 1)] = p3;
+    }
+}
+
+// fast path, rare: a cell ends up with 7 or 8 disks (or more: dropped), but slots 6 and 7 exist only
+// in HBM.  Finds the immigrants that did not fit (the `first` earlier ones are placed), writes the
+// cell's P3 chunk to HBM, stamps the crowded-cell flags and leaves the sign of y5 set for the store.
+// Deliberately not inlined: nothing of it may cost the common path a register.
+__device__ __noinline__ int shift_overflow3(int F, float4 ux03, float2 ux45, float4 uy03, float2 uy45, int ucnt,
+                                            float d, float w, float sshift, int first, int n_total, float *y5,
+                                            int owned, float4 *dout, const Geom4 *gp, const SweepArgs *ap,
+                                            int X, int Y)
+{
+    const float ux[6] = { ux03.x, ux03.y, ux03.z, ux03.w, ux45.x, ux45.y };
+    const float uy[6] = { uy03.x, uy03.y, uy03.z, uy03.w, uy45.x, uy45.y };
+    float4 p3 = make_float4(kSent, kSent, 0.f, 0.f);
+    int k = 0;
+    for (int i = 0; i < 6; i++) {
+        const float fc = F == 0 ? ux[i] : uy[i], oc = F == 0 ? uy[i] : ux[i];
+        const float D = __fadd_rn(fc, -d);
+        if (i < ucnt && !(D > 0.0f && D <= w)) {
+            const float Ds = __fadd_rn(D, sshift);
+            const float vx = F == 0 ? Ds : oc, vy = F == 0 ? oc : Ds;
+            if (k == first) { p3.x = vx; p3.z = vy; }
+            if (k == first + 1) { p3.y = vx; p3.w = vy; }
+            k++;
+        }
+    }
+    const int n = n_total < PMC_NMAX ? n_total : PMC_NMAX;
+    if (n < PMC_NMAX) p3.w = __int_as_float(n);
+    *y5 = -*y5;                                         // "P3 of this cell is already in HBM"
+    if (owned)
+        crowded_cell_out(dout, ap->flag_out, ap->epoch_out, gp->cps, gp->rows, gp->wrap_y, gp->CH, gp->FW, X, Y, 1, p3);
+    return n_total - n;                                 // dropped
 }
 
 // everything one CTA knows about its tile
@@ -196,6 +260,7 @@ struct TileCtx {
     int xs;                 // region column i is staged column i + xs
     int ox0, oy0;           // region coordinates of the owned tile's corner
     int nox, noy;           // owned extent after clipping at the box / slab edge
+    int X0, Y0;             // internal array coordinates of region (0, 0)
 };
 
 // ---- one colour: one thread per active cell (subsweep.h:242-245), own cell in registers
@@ -311,21 +376,22 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     if (NS == 8) pown[3 * PLC] = make_float4(ox[6], ox[7], oy[6], oy[7]);
 }
 
-// ---- shiftCells(f, d) of this sweep for the owned cells, in place (plain plane order out)
-template <int NS, int TX, int TY, bool UNROLL>
-__device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const SweepArgs &a, float w, int sdir,
-                                           int tid, Counters *ctr)
+// ---- shiftCells(f, d) of this sweep for the owned cells, in place (pair order out)
+template <int NS, int TX, int TY, int NPL>
+__device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
+                                           float4 *__restrict__ dout, int sdir, int tid, Counters *ctr)
 {
     using TL = Tile4<TX, TY>;
-    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC, THREADS = TL::THREADS;
-    const float d = a.shift_d;
+    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
+    const float d = a.shift_d, w = g.w;
     const float sshift = __fmul_rn(w, (float)sdir);                 // shiftCells.h:84-86
-    // One thread owns a strip of K consecutive owned cells along the shift axis and walks it
-    // from the downstream end to the upstream end: cell u is rewritten only after raw cell
-    // u+1 has been read.  The raw cell after the strip (next strip, or the extra upstream
-    // row / column) is read before the barrier.
-    constexpr int SEG1 = THREADS / TX, K1 = (TY + SEG1 - 1) / SEG1;     // f = 1: column strips of K1 rows
-    constexpr int SEG0 = THREADS / TY < 8 ? THREADS / TY : 8, K0 = (TX + SEG0 - 1) / SEG0;   // f = 0: row strips of K0 columns
+    // One thread owns a strip of K consecutive owned cells along the shift axis (cell 0 at the
+    // downstream end) and walks it from the upstream end down: before the barrier it reads its
+    // last cell and the raw cell after the strip (first cell of the next strip, or the extra
+    // upstream row / column); cell u is then rewritten with raw u as `own` and raw u+1, still
+    // in registers, as `up`.  Only two cells are ever live in registers.
+    constexpr int SEG1 = kNT / TX, K1 = (TY + SEG1 - 1) / SEG1;     // f = 1: column strips of K1 rows
+    constexpr int SEG0 = kNT / TY < 8 ? kNT / TY : 8, K0 = (TX + SEG0 - 1) / SEG0;   // f = 0: row strips of K0 columns
     int i0, j0, len, di, dj;
     if (a.shift_f == 1) {
         const int seg = tid / TX, col = tid - seg * TX, k0 = seg * K1;
@@ -344,69 +410,162 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const S
     };
     auto load_cell = [&](int i, int j, CellRegs &c) {           // P0..P3 -> plain x / y registers
         const float4 *p = cell_ptr(i, j);
-        const float4 p0 = p[0], p1 = p[PLC], p2 = p[2 * PLC];
+        const float4 p0 = p[0], p1 = p[PLC];
         c.x03 = p0; c.y03 = make_float4(p1.x, p1.y, p1.z, fabsf(p1.w));
         if (NS == 8) {
-            const float4 p3 = p[3 * PLC];
+            const float4 p2 = p[2 * PLC], p3 = p[3 * PLC];
             c.x47 = make_float4(p2.x, p2.y, p3.x, p3.y); c.y47 = make_float4(p2.z, p2.w, p3.z, p3.w);
             c.cnt = decode_cnt8(p3);
         } else {
             // NS = 6 / 4: the higher slots are known to be unused in this tile
+            const float4 p2 = p[2 * PLC];
             c.x47 = NS == 6 ? make_float4(p2.x, p2.y, kSent, kSent) : make_float4(kSent, kSent, kSent, kSent);
             c.y47 = NS == 6 ? make_float4(p2.z, p2.w, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
             c.cnt = decode_cnt6(p2);
         }
     };
-    CellRegs cur, edge;
+    const unsigned sdump = smem_u32(sm + PLC + TL::PLB);            // 16 unused bytes behind plane 1
+    CellRegs cur, upc;
     if (len > 0) {
-        load_cell(i0, j0, cur);
-        load_cell(i0 + len * di, j0 + len * dj, edge);
+        load_cell(i0 + (len - 1) * di, j0 + (len - 1) * dj, cur);
+        load_cell(i0 + len * di, j0 + len * dj, upc);
     }
     __syncthreads();
     constexpr int KMAX = K0 > K1 ? K0 : K1;
-    // UNROLL: the walk is unrolled (no register moves between iterations); the persistent kernel,
-    // which carries more live state, keeps it rolled to stay spill-free at 80 registers
-#pragma unroll(UNROLL ? KMAX : 1)
-    for (int u = 0; u < KMAX; u++) {
-        if (u < len) {
+#pragma unroll
+    for (int v = 0; v < KMAX; v++) {
+        const int u = len - 1 - v;
+        if (u >= 0) {
             const int i = i0 + u * di, j = j0 + u * dj;
-            CellRegs up = edge;
-            if (u + 1 < len) load_cell(i + di, j + dj, up);
             float4 *p = cell_ptr(i, j);
-            p[0] = make_float4(kSent, kSent, kSent, kSent);
-            p[PLC] = make_float4(kSent, kSent, kSent, kSent);
-            p[2 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
-            p[3 * PLC] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float *fx = reinterpret_cast<float *>(p);
-            int dropped, nNew;
-            if (a.shift_f == 0) nNew = shift_into_tile<NS, 0, PLC>(cur, up, d, w, sshift, fx, &dropped);
-            else nNew = shift_into_tile<NS, 1, PLC>(cur, up, d, w, sshift, fx, &dropped);
-            // in-band counts (plain order: y5 = plane 3 word 1, y7 = plane 3 word 3)
-            if (nNew < PMC_NMAX) fx[3 * PLC * 4 + 3] = __int_as_float(nNew);
-            if (nNew < 6) fx[3 * PLC * 4 + 1] = __int_as_float(nNew);
-            if (nNew >= 5) fx[2 * PLC * 4 + 3] = -fx[2 * PLC * 4 + 3];      // "5 or more" flag: sign of y3
+            const float4 empty2 = make_float4(kSent, 0.f, kSent, 0.f);      // two unused slots in pair order
+#pragma unroll
+            for (int c = 0; c < NPL; c++) p[c * PLC] = empty2;
+            int n_own, dropped = 0;
+            int nNew = a.shift_f == 0 ? shift_into_tile<NS, 0, NPL, PLC>(cur, upc, d, w, sshift, smem_u32(p), sdump, n_own)
+                                      : shift_into_tile<NS, 1, NPL, PLC>(cur, upc, d, w, sshift, smem_u32(p), sdump, n_own);
+            // in-band counts and flags, pair order: y3 = chunk 1 word 3, y5 = chunk 2 word 3, y7 = chunk 3 word 3
+            float *fw = reinterpret_cast<float *>(p);
+            const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
+            if (nNew > 2 * NPL) {                       // rare: more disks than staged slots
+                if (NPL == 3) {
+                    constexpr int PSI = PLC * 16;
+                    const int placed_own = 2 * (n_own / PSI) + ((n_own % PSI) ? 1 : 0);
+                    dropped = shift_overflow3(a.shift_f, upc.x03, make_float2(upc.x47.x, upc.x47.y), upc.y03,
+                                              make_float2(upc.y47.x, upc.y47.y), upc.cnt, d, w, sshift, 2 * NPL - placed_own,
+                                              nNew, fw + 2 * PLC * 4 + 3, owned, dout, &g, &a, t.X0 + i, t.Y0 + j);
+                } else dropped = nNew - 2 * NPL;
+                nNew -= dropped;
+            }
+            if (nNew >= 5) fw[PLC * 4 + 3] = -fw[PLC * 4 + 3];              // "5 or more" flag: sign of y3
+            if (nNew < 6) fw[2 * PLC * 4 + 3] = __int_as_float(nNew);
+            if (NPL == 4) {
+                if (nNew < PMC_NMAX) fw[3 * PLC * 4 + 3] = __int_as_float(nNew);
+                if (nNew >= 7 && owned)
+                    crowded_cell_out(dout, a.flag_out, a.epoch_out, g.cps, g.rows, g.wrap_y, g.CH, g.FW,
+                                     t.X0 + i, t.Y0 + j, 0, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
             if (dropped) {
                 atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
-                if ((unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy)
-                    atomicAdd(&ctr->lost, (unsigned long long)dropped);
+                if (owned) atomicAdd(&ctr->lost, (unsigned long long)dropped);
             }
-            cur = up;
+            if (u > 0) {
+                upc = cur;
+                load_cell(i - di, j - dj, cur);
+            }
         }
     }
     __syncthreads();
 }
 
-// ---- one tile of one sweep: stage, 4 colours, shiftCells, store.  tbx / tby = tile column / row;
-// `phase` = parity of the mbarrier phase this staging completes (the barrier is reused by
-// the persistent kernel); pf_* describe the launch grid for the L2 prefetch (pf_n = 0: none).
-template <int TX, int TY, bool UNROLL_SHIFT>
-__device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *__restrict__ dout, const Geom4 &g,
+// ---- owned cells -> HBM (+ periodic images into the margins).  thread -> fixed (chunk column h,
+// parity, plane pair), rows strided: a warp stores runs of TX/2 consecutive float4.  After the
+// shift the staged cells are in pair order and are converted to P0..P3 here: the thread of plane
+// pair 0 reads chunks 0, 1 and writes P0, P1; the thread of pair 1 reads chunks 2 (, 3), writes P2, P3.
+template <int TX, int TY, int NPL>
+__device__ __forceinline__ void store_pass(const float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
+                                           float4 *__restrict__ dout, bool pair_order, int tbx, int tby, int tid)
+{
+    using TL = Tile4<TX, TY>;
+    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC, HX = TX / 2;
+    constexpr int RSTEP = kNT / (4 * HX);                          // threads beyond RSTEP * 4 * HX do not store
+    const int cps = g.cps;
+    const int h = tid % HX, pr = (tid / HX) & 1, pp = (tid / (2 * HX)) & 1, rg = tid / (4 * HX);
+    const int ox = 2 * h + pr;                                      // owned column (parity == internal column parity)
+    const int ux = tbx * TX + ox, uy0 = tby * TY;
+    if (!(ox < t.nox && rg < RSTEP)) return;
+    const int is = t.ox0 + ox + t.xs;
+    unsigned src = smem_u32(sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH + 2 * pp * PLC);
+    const long long ps = (long long)2 * g.CH;                       // float4 chunks between planes
+    const long long rstride = 4 * ps;                               // ... between internal rows
+    float4 *dst = dout + ((long long)(kMY + uy0 + rg) * 4 + 2 * pp) * ps + (long long)pr * g.CH + ((kMX + ux) >> 1);
+    // periodic image of this column inside the margins (cps is even: parity is kept)
+    const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);
+    const bool yedge = g.wrap_y && (uy0 < kMY || uy0 + t.noy > g.rows - kMY);
+    // one cell: the two planes of this thread's pair (q1 unset: the shift already put P3 into HBM)
+    auto fetch = [&](float4 &q0, float4 &q1) -> bool {
+        const float4 c0 = lds128<0>(src);
+        float4 c1 = make_float4(kSent, kSent, 0.f, 0.f);
+        if (NPL == 4 || pp == 0) c1 = lds128<PLC * 16>(src);
+        bool q1_valid = true;
+        if (pp == 0) {
+            q0 = pair_order ? make_float4(c0.x, c0.z, c1.x, c1.z) : c0;
+            q1 = pair_order ? make_float4(c0.y, c0.w, c1.y, c1.w) : c1;
+        } else {
+            q0 = pair_order ? make_float4(c0.x, c0.z, c0.y, c0.w) : c0;
+            if (NPL == 4) q1 = pair_order ? make_float4(c1.x, c1.z, c1.y, c1.w) : c1;
+            else {
+                // fast path: at most 6 disks came in; 7 or 8 can go out only through the shift,
+                // which then wrote P3 itself and left the sign of y5 set
+                if (q0.y < kSentTest && q0.w < 0.0f) { q0.w = -q0.w; q1_valid = false; }
+                q1 = make_float4(kSent, kSent, 0.f, __int_as_float(decode_cnt6(q0)));
+            }
+        }
+        return q1_valid;
+    };
+    if (!ximg && !yedge && pair_order) {
+#pragma unroll 2
+        for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
+            float4 q0, q1;
+            const bool v1 = fetch(q0, q1);
+            dst[0] = q0;
+            if (NPL == 4 || v1) dst[ps] = q1;
+            src += RSTEP * PITCH * 16; dst += RSTEP * rstride;
+        }
+    } else {
+#pragma unroll 1
+        for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
+            float4 q0, q1;
+            const bool v1 = fetch(q0, q1);
+            const int uy = uy0 + oyy;
+            // counts do not change without a shift: the flag of a crowded cell is carried over
+            if (NPL == 4 && !pair_order && pp == 1 && q1.x < kSentTest)
+                crowded_cell_out(dout, a.flag_out, a.epoch_out, cps, g.rows, g.wrap_y, g.CH, g.FW, kMX + ux, kMY + uy, 0, q1);
+            const int yimg = g.wrap_y ? (uy < kMY ? g.rows : (uy >= g.rows - kMY ? -g.rows : 0)) : 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (((q & 1) && !ximg) || ((q & 2) && !yimg)) continue;
+                float4 *di = dst + ((q & 1) ? ximg : 0) + ((q & 2) ? (long long)yimg * rstride : 0);
+                di[0] = q0;
+                if (NPL == 4 || v1) di[ps] = q1;
+            }
+            src += RSTEP * PITCH * 16; dst += RSTEP * rstride;
+        }
+    }
+}
+
+// ---- one tile of one sweep: stage, 4 colours, shiftCells, store.  tbx / tby = tile column / row
+// in the TX x TY tiling; `phase` = parity of the mbarrier phase this staging completes.
+// NPL = 3 is the fast path: it first looks up the crowded-cell flags of the blocks its box
+// touches and returns true, having done nothing, when one is set.
+template <int TX, int TY, int NPL>
+__device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *__restrict__ dout, const Geom4 &g,
                                              const SweepArgs &a, Counters *ctr, int tbx, int tby,
-                                             float4 *sm, uint64_t *mbar, unsigned phase,
+                                             float4 *sm, uint64_t *mbar, unsigned phase, bool prefetch,
                                              unsigned &my_trials, unsigned &my_acc)
 {
     using TL = Tile4<TX, TY>;
-    constexpr int H = TL::H, HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC, NAX = TL::NAX, THREADS = TL::THREADS;
+    constexpr int H = TL::H, PLC = TL::PLC, NAX = TL::NAX;
     const int tid = threadIdx.x;
     const int cps = g.cps;
 
@@ -419,17 +578,18 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
     t.RX = TX + 2 * H + exl + exh; t.RY = TY + 2 * H + eyl + eyh;
     t.rx0 = tbx * TX - H - exl;
     t.ry0 = tby * TY - H - eyl;
-    const int X0 = t.rx0 + kMX, Y0 = t.ry0 + kMY;   // region (0, 0) in internal array coordinates (>= 0)
-    t.xs = X0 & 1;
+    t.X0 = t.rx0 + kMX; t.Y0 = t.ry0 + kMY;         // region (0, 0) in internal array coordinates (>= 0)
+    t.xs = t.X0 & 1;
     t.ox0 = H + exl; t.oy0 = H + eyl;
     t.nox = min(TX, cps - tbx * TX); t.noy = min(TY, g.rows - tby * TY);
+    const int Xb0 = t.X0 - t.xs;                    // first column of the staged box
 
-    // ------------------------------------------------------------ stage the tile: 4 TMA boxes
+    // ------------------------------------------------------------ stage the tile: one TMA box per plane
     if (tid == 0) {
-        mbar_expect_tx(mbar, (unsigned)(4 * TL::PLB * 16));
+        mbar_expect_tx(mbar, (unsigned)(NPL * TL::PLB * 16));
 #pragma unroll
-        for (int p = 0; p < 4; p++) tma_load_4d(sm + p * PLC, tmap_p, 4 * ((X0 - t.xs) >> 1), 0, p, Y0, mbar);
-        if (a.prefetch_ahead > 0) {
+        for (int p = 0; p < NPL; p++) tma_load_4d(sm + p * PLC, tmap_p, 4 * (Xb0 >> 1), 0, p, t.Y0, mbar);
+        if (prefetch && a.prefetch_ahead > 0) {
             // warm L2 for the tile a CTA slot freed by this wave will stage (blocks are issued in order)
             const int nb = blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
             if (nb < (int)(gridDim.x * gridDim.y)) {
@@ -437,33 +597,53 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
                 const int by2 = gr2 < a.by_n1 ? gr2 + a.by_off : gr2 - a.by_n1 + a.by_off2;
                 const int X2 = bx2 * TX - H - exl + kMX, Y2 = by2 * TY - H - eyl + kMY;
 #pragma unroll
-                for (int p = 0; p < 4; p++) tma_prefetch_4d(tmap_p, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
+                for (int p = 0; p < NPL; p++) tma_prefetch_4d(tmap_p, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
             }
         }
-        mbar_wait(mbar, phase);     // one poller; the others observe the completed phase once
     }
-    __syncthreads();
+    int crowded = 0;
+    if (NPL == 3) {
+        // at most 6 x 5 flag blocks under the 36 x 33 box: one lane each, while the TMA is in flight
+        if (tid < 30 && !(a.dbg_skip & 32)) {
+            const int bx = (Xb0 >> kFB) + tid % 6, by = (t.Y0 >> kFB) + tid / 6;
+            if (bx <= ((Xb0 + TL::PITCH - 1) >> kFB) && by <= ((t.Y0 + TL::SYB - 1) >> kFB))
+                crowded = __ldg(a.flag_in + by * g.FW + bx) == a.epoch_in;
+        }
+        static_assert(NPL != 3 || (TL::PITCH + 6) / 8 + 1 <= 6 && (TL::SYB + 6) / 8 + 1 <= 5, "flag lanes");
+        if (a.dbg_skip & 8) crowded = 1;
+    }
+    if (tid == 0) mbar_wait(mbar, phase);           // one poller; the others observe the completed phase once
+    crowded = __syncthreads_or(crowded);
     mbar_wait(mbar, phase);
+    if (NPL == 3 && crowded) return true;
 
-    // does any staged cell hold 7 or 8 disks (x6 in use), or 5 or 6 (x4 in use)?  Otherwise P3
-    // (P3 and P2) are never needed: bit 1 / bit 0 of `big`
+    // which slots are in use anywhere in the staged box?  x6 (7 or 8 disks: NS = 8, only possible
+    // with P3 staged), x4 (5 or 6: NS = 6), else NS = 4: bit 1 / bit 0 of `big`
     int big = 0;
-    {
+    if (NPL == 4) {
         const float *x4 = reinterpret_cast<const float *>(sm + 2 * PLC);
         const float *x6 = reinterpret_cast<const float *>(sm + 3 * PLC);
         if (g.try_ns4) {
 #pragma unroll 1
-            for (int c = tid; c < TL::PLB; c += THREADS)
+            for (int c = tid; c < TL::PLB; c += kNT)
                 big |= (x6[c * 4] < kSentTest ? 2 : 0) | (x4[c * 4] < kSentTest ? 1 : 0);
         } else {            // dense system: no tile will qualify for NS = 4, scan one plane only
 #pragma unroll 1
-            for (int c = tid; c < TL::PLB; c += THREADS) big |= x6[c * 4] < kSentTest ? 2 : 1;
+            for (int c = tid; c < TL::PLB; c += kNT) big |= x6[c * 4] < kSentTest ? 2 : 1;
+        }
+        big = __syncthreads_or(big & 2) ? 2 : (__syncthreads_or(big & 1) ? 1 : 0);
+    } else {
+        big = 1;
+        if (g.try_ns4) {
+            const float *x4 = reinterpret_cast<const float *>(sm + 2 * PLC);
+            big = 0;
+#pragma unroll 1
+            for (int c = tid; c < TL::PLB; c += kNT) big |= x4[c * 4] < kSentTest ? 1 : 0;
+            big = __syncthreads_or(big);
         }
     }
-    big = __syncthreads_or(big & 2) ? 2 : (__syncthreads_or(big & 1) ? 1 : 0);
-    if (a.dbg_skip & 8) big = 2;
     if ((a.dbg_skip & 16) && big == 0) big = 1;
-    const bool ns8 = big == 2, ns4 = big == 0;
+    const bool ns8 = NPL == 4 && big == 2, ns4 = big == 0;
 
     // ------------------------------------------------------------ the four sub-sweeps
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
@@ -480,7 +660,7 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
                 colour_pass<6, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
                 __syncthreads();
             }
-        } else {
+        } else if (NPL == 4) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
                 colour_pass<8, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
@@ -491,65 +671,14 @@ __device__ __forceinline__ void process_tile(const CUtensorMap *tmap_p, float4 *
 
     // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
     if (do_shift) {
-        if (ns4) shift_pass<4, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
-        else if (!ns8) shift_pass<6, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
-        else shift_pass<8, TX, TY, UNROLL_SHIFT>(sm, t, a, g.w, sdir, tid, ctr);
+        if (ns4) shift_pass<4, TX, TY, NPL>(sm, t, g, a, dout, sdir, tid, ctr);
+        else if (!ns8) shift_pass<6, TX, TY, NPL>(sm, t, g, a, dout, sdir, tid, ctr);
+        else if (NPL == 4) shift_pass<8, TX, TY, NPL>(sm, t, g, a, dout, sdir, tid, ctr);
     }
 
-    // ------------------------------------------------------------ owned tile -> HBM (+ periodic images into the margins)
-    if (!(a.dbg_skip & 4)) {
-        // thread -> fixed (chunk column h, parity, plane), rows strided: a warp stores runs of
-        // TX/2 consecutive float4.  After the shift the staged cells are in plain plane order
-        // (x0-3 | x4-7 | y0-3 | y4-7) and are converted to P0..P3 here.
-        constexpr int HX = TX / 2, RSTEP = THREADS / (8 * HX);   // threads beyond RSTEP * 8 * HX do not store
-        const int h = tid % HX, pr = (tid / HX) & 1, pl = (tid / (2 * HX)) & 3, rg = tid / (8 * HX);
-        const int ox = 2 * h + pr;                                  // owned column (parity == internal column parity)
-        const int ux = tbx * TX + ox, uy0 = tby * TY;
-        if (ox < t.nox && rg < RSTEP) {
-            const int is = t.ox0 + ox + t.xs;
-            const float4 *cell0 = sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH;
-            // source of output plane pl: P0 <- x03, P1 <- y03, P2 <- x47.xy y47.xy, P3 <- x47.zw y47.zw
-            const float4 *src = cell0 + (do_shift ? (pl == 0 ? 0 : (pl == 1 ? 2 : 1)) : pl) * PLC;
-            const int half = (pl == 3) ? 2 : 0;                     // float offset of the pair inside x47 / y47
-            const bool split = do_shift && pl >= 2;
-            auto fetch = [&](const float4 *s) -> float4 {
-                if (!split) return *s;
-                const float2 xa = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(s) + half);
-                const float2 ya = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(s + 2 * PLC) + half);
-                return make_float4(xa.x, xa.y, ya.x, ya.y);
-            };
-            const long long rstride = (long long)8 * g.CH;          // float4 chunks per internal row
-            float4 *dst = dout + ((long long)(kMY + uy0 + rg) * 4 + pl) * 2 * g.CH + (long long)pr * g.CH + ((kMX + ux) >> 1);
-            // periodic image of this column inside the margins (cps is even: parity is kept)
-            const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);
-            const bool yedge = g.wrap_y && (uy0 < kMY || uy0 + t.noy > g.rows - kMY);
-            if (!ximg && !yedge) {
-#pragma unroll 2
-                for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
-                    *dst = fetch(src);
-                    src += RSTEP * PITCH; dst += RSTEP * rstride;
-                }
-            } else {
-#pragma unroll 1
-                for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
-                    const float4 v = fetch(src);
-                    const int uy = uy0 + oyy;
-                    dst[0] = v;
-                    if (ximg) dst[ximg] = v;
-                    if (g.wrap_y) {
-                        const int yimg = uy < kMY ? g.rows : (uy >= g.rows - kMY ? -g.rows : 0);
-                        if (yimg) {
-                            float4 *di = dst + (long long)yimg * rstride;
-                            di[0] = v;
-                            if (ximg) di[ximg] = v;
-                        }
-                    }
-                    src += RSTEP * PITCH; dst += RSTEP * rstride;
-                }
-            }
-        }
-    }
-
+    // ------------------------------------------------------------ owned tile -> HBM
+    if (!(a.dbg_skip & 4)) store_pass<TX, TY, NPL>(sm, t, g, a, dout, do_shift, tbx, tby, tid);
+    return false;
 }
 
 // acceptance counts reduced warp-level, one atomic per warp (kernel.cu:228,413 accept_counter)
@@ -563,113 +692,73 @@ __device__ __forceinline__ void flush_counters(Counters *ctr, unsigned my_trials
     }
 }
 
-// ---- one launch = one sweep (slab runs, and the fallback of the persistent kernel)
-template <int TX, int TY, int MINB>
-__global__ void __launch_bounds__(Tile4<TX, TY>::THREADS, MINB)
-sweep4_kernel(const __grid_constant__ CUtensorMap tmap, float4 *__restrict__ dout, const Geom4 g,
-              const SweepArgs a, Counters *ctr)
+constexpr int kTY = 24, kTYS = 12;      // tile height; height of the two half tiles a crowded tile is split into
+
+// ---- crowded tile (a staged cell holds 7 or 8 disks): all four planes, half the rows at a time, in the
+// shared memory of the fast tile.  Rare, and deliberately NOT inlined: the fast path keeps its own
+// register allocation (64 registers without spills).  Returns (trials << 32) | accepted of this thread.
+template <int TX>
+__device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_half, float4 *dout, const Geom4 *gp,
+                                                        const SweepArgs *ap, Counters *ctr, int tbx, int tby,
+                                                        float4 *sm, uint64_t *mbar_fast)
 {
-    using TL = Tile4<TX, TY>;
+    using TS = Tile4<TX, kTYS>;
+    uint64_t *mbar2 = reinterpret_cast<uint64_t *>(sm + TS::PLB);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar_fast)) : "memory");
+        mbar_init(mbar2, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned my_trials = 0, my_acc = 0;
+#pragma unroll 1
+    for (int half = 0; half < kTY / kTYS; half++) {
+        const int tbys = tby * (kTY / kTYS) + half;
+        if (tbys * kTYS < gp->rows)
+            process_tile<TX, kTYS, 4>(tmap_half, dout, *gp, *ap, ctr, tbx, tbys, sm, mbar2, (unsigned)(half & 1), false,
+                                      my_trials, my_acc);
+        __syncthreads();                        // every thread is done with the tile before the next box lands on it
+        if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    return ((unsigned long long)my_trials << 32) | my_acc;
+}
+
+// ---- one launch = one sweep.  FAST: 3 planes staged, 4 CTAs per SM, crowded tiles re-done as two
+// half tiles with 4 planes in the same shared memory.  !FAST: 4 planes, 3 CTAs per SM, no flag
+// lookup (slab boundary rows, whose ghost rows carry no flags).
+template <int TX, int MINB, bool FAST>
+__global__ void __launch_bounds__(kNT, MINB)
+sweep4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
+              float4 *__restrict__ dout, const __grid_constant__ Geom4 g, const __grid_constant__ SweepArgs a, Counters *ctr)
+{
+    using TL = Tile4<TX, kTY>;
+    using TS = Tile4<TX, kTYS>;
+    static_assert(4 * TS::PLANE_BYTES <= 3 * TL::PLANE_BYTES, "the half tiles reuse the fast tile's shared memory");
     extern __shared__ __align__(128) float4 sm[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + 4 * TL::PLC);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + TL::PLB);
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // tile row (a launch may cover one or two bands of rows)
     const int tby = (int)blockIdx.y < a.by_n1 ? (int)blockIdx.y + a.by_off : (int)blockIdx.y - a.by_n1 + a.by_off2;
+    const int tbx = (int)blockIdx.x;
     unsigned my_trials = 0, my_acc = 0;
-    process_tile<TX, TY, true>(&tmap, dout, g, a, ctr, (int)blockIdx.x, tby, sm, mbar, 0u, my_trials, my_acc);
+    if (!FAST) {
+        process_tile<TX, kTY, 4>(&tmap, dout, g, a, ctr, tbx, tby, sm, mbar, 0u, true, my_trials, my_acc);
+    } else if (process_tile<TX, kTY, 3>(&tmap, dout, g, a, ctr, tbx, tby, sm, mbar, 0u, true, my_trials, my_acc)) {
+        const unsigned long long r = crowded_tile<TX>(&tmap_half, dout, &g, &a, ctr, tbx, tby, sm, mbar);
+        my_trials += (unsigned)(r >> 32); my_acc += (unsigned)r;
+    }
     flush_counters(ctr, my_trials, my_acc);
-}
-
-// ---- persistent kernel: n_steps sweeps in ONE cooperative launch (single GPU).  CTA c owns
-// tiles c, c + G, c + 2G, ... of every sweep; there is no grid-wide barrier between sweeps:
-// a tile of sweep s starts as soon as the (up to 4 x 4, normally 3 x 3) tiles of sweep s-1
-// that produced its staged box - and that were the last readers of the cells it is about to
-// overwrite in the other ping-pong buffer - have published done[tile] >= s.  This removes the
-// per-sweep launch and the idle tail of the last partial wave (~5 % at N = 2^24).
-struct StepArgs { unsigned offmask, sweep_lo, sweep_hi; int shift_f; float shift_d; };
-constexpr int kStepCap = 1024;
-// per-sweep arguments of the batch in flight: constant memory, indexed by the (warp-uniform) sweep
-// counter, so they live in the uniform datapath instead of in vector registers
-__constant__ StepArgs c_steps[kStepCap];
-
-__device__ __forceinline__ int ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <int TX, int TY, int MINB>
-__global__ void __launch_bounds__(Tile4<TX, TY>::THREADS, MINB)
-sweep4_persistent(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                  float4 *__restrict__ buf0, float4 *__restrict__ buf1, const Geom4 g,
-                  int n_steps, int src0, int *done, Counters *ctr, int dbg)
-{
-    using TL = Tile4<TX, TY>;
-    extern __shared__ __align__(128) float4 sm[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + 4 * TL::PLC);
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    const int gx = (g.cps + TX - 1) / TX, gy = (g.rows + TY - 1) / TY, ntiles = gx * gy;
-    unsigned phase = 0;
-#pragma unroll 1
-    for (int s = 0; s < n_steps; s++) {
-        SweepArgs sa;
-        sa.offmask = c_steps[s].offmask; sa.sweep_lo = c_steps[s].sweep_lo; sa.sweep_hi = c_steps[s].sweep_hi;
-        sa.shift_on = 1; sa.shift_f = c_steps[s].shift_f; sa.shift_d = c_steps[s].shift_d;
-        sa.sanitize_in = 0; sa.by_off = 0; sa.by_n1 = 0x7fffffff; sa.by_off2 = 0; sa.prefetch_ahead = 0; sa.dbg_skip = dbg;
-        const int src = (src0 + s) & 1;
-#pragma unroll 1
-        for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
-            // every other sweep starts half a grid away: the tiles a CTA runs first never depend on
-            // the tiles the previous sweep finished last (first and last tile rows are periodic
-            // neighbours), so there is no idle tail between sweeps
-            int tile = it + ((s & 1) ? ntiles / 2 : 0);
-            tile -= tile >= ntiles ? ntiles : 0;
-            const int tby = tile / gx, tbx = tile - tby * gx;
-            if (s > 0 && tid < 16) {
-                // producers (sweep s-1) of every cell this tile stages or overwrites: the tiles under
-                // the four corner-ish columns / rows of the staged box, wrapped like the images
-                const int x0 = tbx * TX, y0 = tby * TY;
-                const int xl = min(x0 + TX, g.cps) - 1, yl = min(y0 + TY, g.rows) - 1;
-                const int sx = tid & 3, sy = tid >> 2;
-                int cx = sx == 0 ? x0 - kMX : (sx == 1 ? x0 : (sx == 2 ? xl : xl + kMX));
-                int cy = sy == 0 ? y0 - kMY : (sy == 1 ? y0 : (sy == 2 ? yl : yl + kMY));
-                cx += cx < 0 ? g.cps : 0; cx -= cx >= g.cps ? g.cps : 0;
-                cy += cy < 0 ? g.rows : 0; cy -= cy >= g.rows ? g.rows : 0;
-                const int *flag = done + (cy / TY) * gx + cx / TX;
-                while (ld_acquire(flag) < s) __nanosleep(64);
-            }
-            __syncthreads();
-            if (tid == 0) asm volatile("fence.proxy.async;" ::: "memory");   // the TMA reads what the producers stored
-            unsigned my_trials = 0, my_acc = 0;
-            process_tile<TX, TY, false>(src ? &tm1 : &tm0, src ? buf0 : buf1, g, sa, ctr, tbx, tby, sm, mbar, phase, my_trials, my_acc);
-            flush_counters(ctr, my_trials, my_acc);
-            phase ^= 1u;
-            // bar.sync orders every thread's stores before thread 0's release (cumulative at gpu scope);
-            // it also frees the shared memory for the next box
-            __syncthreads();
-            if (tid == 0) st_release(done + tile, s + 1);
-        }
-    }
 }
 
 // ------------------------------------------------------------------ caller layout <-> internal layout
 // caller: disk float[cell][2][8] + int16 n[cell] (include/pmc.h).  One thread per (internal
 // cell, plane); margins are filled with the periodic images, everything beyond with empty cells.
 __global__ void import4_kernel(const float *__restrict__ disk, const int16_t *__restrict__ n,
-                               float4 *__restrict__ out, Geom4 g, int ghost)
+                               float4 *__restrict__ out, Geom4 g, int ghost, unsigned *__restrict__ flags, unsigned epoch)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int cols = 2 * g.CH;
@@ -712,6 +801,7 @@ __global__ void import4_kernel(const float *__restrict__ disk, const int16_t *__
             // in-band count (the caller's unused slots may hold garbage: never copied)
             if (pl == 2 && cnt < 6) v[3] = __int_as_float(cnt);
             if (pl == 3 && cnt < PMC_NMAX) v[3] = __int_as_float(cnt);
+            if (pl == 3 && cnt >= 7) flags[(Y >> kFB) * g.FW + (X >> kFB)] = epoch;      // crowded cell: P3 must be staged
         }
     }
     out[((long long)(Y * 4 + pl) * 2 + (X & 1)) * g.CH + (X >> 1)] = make_float4(v[0], v[1], v[2], v[3]);
@@ -754,40 +844,31 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-// tile configurations (PMC_TILE4 selects; 1 is the tuned default)
-struct TileCfg { int tx, ty, hb, syb, h; };
-template <int TX, int TY> constexpr TileCfg cfg_of() { return { TX, TY, Tile4<TX, TY>::HB, Tile4<TX, TY>::SYB, Tile4<TX, TY>::H }; }
-constexpr TileCfg kCfgs[] = { cfg_of<24, 40>(), cfg_of<24, 24>(), cfg_of<24, 32>(), cfg_of<24, 48>() };
-// default (index 0): sweeps that shift along y use 26-column tiles (16, 15, 14, 13 active cells
-// per half-warp instead of 15, 14, 13, 12); the staged box is the same, so is the tensor map
-constexpr TileCfg kCfgWideY = cfg_of<26, 40>();
-static_assert(kCfgWideY.hb == kCfgs[0].hb && kCfgWideY.syb == kCfgs[0].syb, "one TMA box for both default tilings");
+// The tiling: 24 x 24 owned cells; sweeps that do not shift along x use 26-column tiles (16, 15,
+// 14, 13 active cells per half-warp instead of 15, 14, 13, 12); the staged box is the same, so is
+// the tensor map.  A second map with the half-height box serves the crowded tiles.
+constexpr int kTXN = 24, kTXW = 26;
+static_assert(Tile4<kTXN, kTY>::HB == Tile4<kTXW, kTY>::HB && Tile4<kTXN, kTYS>::HB == Tile4<kTXW, kTYS>::HB,
+              "one TMA box for both tile widths");
 
-int tile_index()
+template <int TX, int MINB, bool FAST>
+cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a_in,
+                       Counters *ctr, cudaStream_t st, int by0, int nby, int by1, int nby1)
 {
-    static const int idx = [] {
-        const char *e = getenv("PMC_TILE4");
-        const int i = e ? atoi(e) : 1;      // tuned default: 24 / 26 x 24 tiles, 3 CTAs per SM
-        return (i >= 0 && i < (int)(sizeof(kCfgs) / sizeof(kCfgs[0]))) ? i : 1;
-    }();
-    return idx;
-}
-
-template <int TX, int TY, int MINB>
-cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a_in, Counters *ctr,
-                       cudaStream_t st, int by0, int nby, int by1, int nby1)
-{
-    using TL = Tile4<TX, TY>;
-    auto kern = sweep4_kernel<TX, TY, MINB>;
+    using TL = Tile4<TX, kTY>;
+    constexpr int SMEM = (int)((FAST ? 3 : 4) * TL::PLANE_BYTES);
+    auto kern = sweep4_kernel<TX, MINB, FAST>;
     static bool attr_set[64] = { false };           // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const int gy = (g.rows + TY - 1) / TY;
+    const int gy = (g.rows + kTY - 1) / kTY;
     SweepArgs a = a_in;
     a.by_off = by0;
     if (nby <= 0) { a.by_off = 0; nby = gy; }
@@ -796,99 +877,41 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, float4 *dout, const 
     a.by_n1 = nby; a.by_off2 = by1;
     if (nby1 < 0 || by1 + nby1 > gy) nby1 = 0;
     dim3 grid((g.cps + TX - 1) / TX, nby + nby1);
-    kern<<<grid, TL::THREADS, TL::SMEM, st>>>(*(const CUtensorMap *)tmap_in, dout, g, a, ctr);
+    kern<<<grid, kNT, SMEM, st>>>(*(const CUtensorMap *)tmap_in, *(const CUtensorMap *)tmap_half, dout, g, a, ctr);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-// persistent multi-sweep launch (single GPU, default tiling): returns cudaErrorNotSupported when
-// the geometry does not qualify (the caller then launches one kernel per sweep)
-int pmc4_step_capacity() { return kStepCap; }
+int pmc4_tile_count(const Geom4 &g) { return ((g.cps + kTXN - 1) / kTXN) * ((g.rows + kTY - 1) / kTY); }
+int pmc4_tile_rows(const Geom4 &g) { return (g.rows + kTY - 1) / kTY; }
+int pmc4_tile_x() { return kTXN; }
+int pmc4_tile_y() { return kTY; }
 
-// steps_host: n_steps Pmc4Step records (pageable is fine).  The constant bank is shared by every
-// handle of this process on this device: a launch waits for the previous batch to finish.
-cudaError_t pmc4_launch_persistent(const Geom4 &g, const void *tmap0, const void *tmap1, float4 *buf0, float4 *buf1,
-                                   const void *steps_host, int n_steps, int src0, int *done_dev, Counters *ctr,
-                                   int dbg, cudaStream_t st)
+// rows / chunk columns the internal array needs so that every staged box is in bounds, and the
+// extent of the crowded-cell flag grid over it
+void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS, int *FW, int *FH)
 {
-    constexpr int TX = 24, TY = 24, MINB = 3;
-    using TL = Tile4<TX, TY>;
-    if (tile_index() != 1 || !g.wrap_y) return cudaErrorNotSupported;
-    // a clipped last tile narrower than the margin would make the image producers span two tiles
-    const int remx = g.cps % TX, remy = g.rows % TY;
-    if ((remx && remx < kMX) || (remy && remy < kMY) || g.cps < 2 * TX || g.rows < 2 * TY) return cudaErrorNotSupported;
-    auto kern = sweep4_persistent<TX, TY, MINB>;
-    static int grid_max = 0;
-    if (!grid_max) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0, coop = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TL::THREADS, TL::SMEM);
-        if (e != cudaSuccess) return e;
-        if (!coop || per_sm < 1) return cudaErrorNotSupported;
-        grid_max = sms * per_sm;
-    }
-    if (n_steps > kStepCap) return cudaErrorInvalidValue;
-    const int gx = (g.cps + TX - 1) / TX, gy = (g.rows + TY - 1) / TY;
-    const int grid = gx * gy < grid_max ? gx * gy : grid_max;
-    static std::mutex mu;
-    static cudaEvent_t batch_done = nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    cudaError_t e;
-    if (!batch_done) { e = cudaEventCreateWithFlags(&batch_done, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
-    else { e = cudaEventSynchronize(batch_done); if (e != cudaSuccess) return e; }     // c_steps is free again
-    e = cudaMemcpyToSymbolAsync(c_steps, steps_host, (size_t)n_steps * sizeof(StepArgs), 0, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(st);                  // steps_host may be pageable and reused by the caller
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(done_dev, 0, (size_t)gx * gy * sizeof(int), st);
-    if (e != cudaSuccess) return e;
-    CUtensorMap t0 = *(const CUtensorMap *)tmap0, t1 = *(const CUtensorMap *)tmap1;
-    Geom4 gg = g;
-    void *args[] = { &t0, &t1, &buf0, &buf1, &gg, &n_steps, &src0, &done_dev, &ctr, &dbg };
-    e = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(TL::THREADS), args, TL::SMEM, st);
-    if (e != cudaSuccess) return e;
-    return cudaEventRecord(batch_done, st);
-}
-
-int pmc4_tile_count(const Geom4 &g)
-{
-    const TileCfg c = kCfgs[tile_index()];
-    return ((g.cps + c.tx - 1) / c.tx) * ((g.rows + c.ty - 1) / c.ty);
-}
-
-int pmc4_tile_rows(const Geom4 &g) { const int ty = kCfgs[tile_index()].ty; return (g.rows + ty - 1) / ty; }
-
-int pmc4_tile_x() { return kCfgs[tile_index()].tx; }
-int pmc4_tile_y() { return kCfgs[tile_index()].ty; }
-
-// rows / chunk columns the internal array needs so that every staged box is in bounds
-void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS)
-{
-    const TileCfg c = kCfgs[tile_index()];
-    const int gx = (cps + c.tx - 1) / c.tx, gy = (rows + c.ty - 1) / c.ty;
+    using TN = Tile4<kTXN, kTY>;
+    using TW = Tile4<kTXW, kTY>;
+    const int gxn = (cps + kTXN - 1) / kTXN, gxw = (cps + kTXW - 1) / kTXW, gy = (rows + kTY - 1) / kTY;
     // last staged column: kMX + (gx-1)*TX - H - 1 (rounded down to even) + 2*HB - 1
-    int cols = kMX + (gx - 1) * c.tx - c.h + 2 * c.hb + 2;
-    if (tile_index() <= 1) {
-        const int gxw = (cps + kCfgWideY.tx - 1) / kCfgWideY.tx;
-        const int colsw = kMX + (gxw - 1) * kCfgWideY.tx - kCfgWideY.h + 2 * kCfgWideY.hb + 2;
-        cols = colsw > cols ? colsw : cols;
-    }
+    const int cn = kMX + (gxn - 1) * kTXN - TN::H + 2 * TN::HB + 2;
+    const int cw = kMX + (gxw - 1) * kTXW - TW::H + 2 * TW::HB + 2;
+    int cc = cn > cw ? cn : cw;
     const int cols_img = cps + 2 * kMX;
-    const int cc = cols > cols_img ? cols : cols_img;
+    cc = cc > cols_img ? cc : cols_img;
     *CH = (cc + 1) / 2;
-    const int r = kMY + (gy - 1) * c.ty - c.h + c.syb + 1;
+    const int r = kMY + (gy - 1) * kTY - TN::H + TN::SYB + 1;
     const int r_img = rows + 2 * kMY;
     *ROWS = r > r_img ? r : r_img;
+    *FW = ((2 * *CH) >> kFB) + 1;
+    *FH = (*ROWS >> kFB) + 1;
 }
 
-int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g)
+// half = 0: the box of a full tile; 1: the box of a half-height tile (crowded tiles)
+int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g, int half)
 {
-    const TileCfg c = kCfgs[tile_index()];
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -897,9 +920,10 @@ int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g)
         if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)(e != cudaSuccess ? e : cudaErrorNotSupported);
         encode = (EncodeTiledFn)fn;
     }
+    const int hb = Tile4<kTXN, kTY>::HB, syb = half ? Tile4<kTXN, kTYS>::SYB : Tile4<kTXN, kTY>::SYB;
     const cuuint64_t dims[4] = { (cuuint64_t)4 * g.CH, 2, 4, (cuuint64_t)g.ROWS };
     const cuuint64_t strides[3] = { (cuuint64_t)g.CH * 16, (cuuint64_t)g.CH * 32, (cuuint64_t)g.CH * 128 };
-    const cuuint32_t box[4] = { (cuuint32_t)(4 * c.hb), 2, 1, (cuuint32_t)c.syb };
+    const cuuint32_t box[4] = { (cuuint32_t)(4 * hb), 2, 1, (cuuint32_t)syb };
     const cuuint32_t estr[4] = { 1, 1, 1, 1 };
     CUresult r = encode((CUtensorMap *)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -907,10 +931,11 @@ int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g)
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out, cudaStream_t st)
+cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out,
+                               unsigned *flags, unsigned epoch, cudaStream_t st)
 {
     const long long threads = (long long)2 * g.CH * g.ROWS * 4;
-    import4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float *)disk, n, out, g, ghost);
+    import4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float *)disk, n, out, g, ghost, flags, epoch);
     return cudaGetLastError();
 }
 
@@ -921,17 +946,16 @@ cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, floa
     return cudaGetLastError();
 }
 
-cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, float4 *dout, const SweepArgs &a,
-                              Counters *ctr, cudaStream_t st, int by0, int nby, int by1, int nby1)
+// fast = 1: the 3-plane kernel with the crowded-cell flag lookup (tile rows whose boxes hold no
+// ghost rows); 0: the 4-plane kernel
+cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a,
+                              Counters *ctr, cudaStream_t st, int fast, int by0, int nby, int by1, int nby1)
 {
-    switch (tile_index()) {
-    case 1:
-        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 24, 3>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
-        return launch_cfg<26, 24, 3>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
-    case 2: return launch_cfg<24, 32, 2>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
-    case 3: return launch_cfg<24, 48, 1>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
-    default:
-        if (a.shift_on && a.shift_f == 0) return launch_cfg<24, 40, 2>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
-        return launch_cfg<26, 40, 2>(g, tmap_in, dout, a, ctr, st, by0, nby, by1, nby1);
+    const bool narrow = a.shift_on && a.shift_f == 0;       // the extra upstream column needs the 35th region column
+    if (fast) {
+        if (narrow) return launch_cfg<kTXN, 4, true>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
+        return launch_cfg<kTXW, 4, true>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
     }
+    if (narrow) return launch_cfg<kTXN, 3, false>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
+    return launch_cfg<kTXW, 3, false>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
 }

@@ -385,19 +385,45 @@ def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
     assert c["lost"] > 0 and c["status"] & 1
 
 
-def test_experimental_persistent_kernel_is_bit_exact():
-    """PMC_PERSISTENT=1 (off by default): many sweeps in one cooperative launch
-    with per-tile completion flags instead of kernel boundaries.  The switch is read once per
-    process, hence the subprocess."""
+def test_crowded_tile_path_is_bit_exact_on_ordinary_tiles():
+    """PMC_DBG_SKIP=8 sends EVERY tile of the fused sweep down the crowded-tile path (two half-height
+    tiles with all four planes staged) instead of the 3-plane fast path; the result must not change.
+    The switch is read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PMC_PERSISTENT="1", PMC_S="7", PMC_N=str(2 ** 16))
+    env = dict(os.environ, PMC_DBG_SKIP="8", PMC_S="7", PMC_N=str(2 ** 16))
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "debug_v4.py")], env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert "count mismatches 0" in out.stdout and "position mismatches 0" in out.stdout, out.stdout[-1500:]
+
+
+def test_cells_that_become_crowded_on_the_fast_path():
+    """Mildly crowded system (Poisson occupancy, mean 1.0: one cell in 10^4 holds 7 or 8 disks): most tiles hold no cell with 7 or 8
+    disks and run the 3-plane fast path, but shiftCells keeps producing such cells there (their P3
+    chunk goes straight to HBM and the block is flagged for the next sweep), and flagged tiles
+    fall back to the 4-plane half tiles.  20 sweeps, bit-identical to the oracle throughout."""
+    import torch
+    sigma, lam, N = 0.25, 1.0, 2 ** 17
+    phi = lam * np.pi * sigma * sigma / 16.0
+    mc, o = pair(N, sigma_d=sigma, phi=float(phi), cell_w=2.0, move_delta=0.3)
+    rng = np.random.default_rng(5)
+    hl = np.float32(o.g.L / 2)
+    r = (rng.random((2, N), dtype=np.float32) * 2 - 1) * hl * np.float32(0.9999)
+    disk, n = mc.assign(torch.from_numpy(r).cuda())
+    odisk, on = o.assign(r)
+    assert_same_state(disk, n, odisk, on)
+    seen7 = 0
+    for s in range(0, 20, 4):
+        mc.sweep(disk, n, s, 4)
+        o.sweep(odisk, on, s, 4)
+        assert_same_state(disk, n, odisk, on)
+        seen7 += int((on >= 7).sum())
+    assert seen7 > 10 and int((on >= 7).sum()) < on.size // 500
+    c = mc.counters()
+    assert (c["trials"], c["accepted"], c["lost"]) == (o.trials.value, o.accepted.value, o.lost)
 
 
 # ---------------------------------------------------------------- 3-sigma agreement over INDEPENDENT seeds
