@@ -377,7 +377,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
 }
 
 // ---- shiftCells(f, d) of this sweep for the owned cells, in place (pair order out)
-template <int NS, int TX, int TY, int NPL>
+template <int NS, int TX, int TY, int NPL, int F>
 __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
                                            float4 *__restrict__ dout, int sdir, int tid, Counters *ctr)
 {
@@ -392,17 +392,16 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
     // in registers, as `up`.  Only two cells are ever live in registers.
     constexpr int SEG1 = kNT / TX, K1 = (TY + SEG1 - 1) / SEG1;     // f = 1: column strips of K1 rows
     constexpr int SEG0 = kNT / TY < 8 ? kNT / TY : 8, K0 = (TX + SEG0 - 1) / SEG0;   // f = 0: row strips of K0 columns
-    int i0, j0, len, di, dj;
-    if (a.shift_f == 1) {
+    int i0, j0, len;
+    const int di = F == 0 ? sdir : 0, dj = F == 0 ? 0 : sdir;
+    if (F == 1) {
         const int seg = tid / TX, col = tid - seg * TX, k0 = seg * K1;
         len = (seg < SEG1 && k0 < TY) ? min(K1, TY - k0) : 0;
         i0 = t.ox0 + col; j0 = t.oy0 + (sdir > 0 ? k0 : TY - 1 - k0);
-        di = 0; dj = sdir;
     } else {
         const int row = tid / SEG0, seg = tid - row * SEG0, k0 = seg * K0;
         len = (row < TY && k0 < TX) ? min(K0, TX - k0) : 0;
         j0 = t.oy0 + row; i0 = t.ox0 + (sdir > 0 ? k0 : TX - 1 - k0);
-        di = sdir; dj = 0;
     }
     auto cell_ptr = [&](int i, int j) -> float4 * {
         const int is = i + t.xs;
@@ -431,7 +430,7 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
         load_cell(i0 + len * di, j0 + len * dj, upc);
     }
     __syncthreads();
-    constexpr int KMAX = K0 > K1 ? K0 : K1;
+    constexpr int KMAX = F == 0 ? K0 : K1;
 #pragma unroll
     for (int v = 0; v < KMAX; v++) {
         const int u = len - 1 - v;
@@ -442,8 +441,7 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
 #pragma unroll
             for (int c = 0; c < NPL; c++) p[c * PLC] = empty2;
             int n_own, dropped = 0;
-            int nNew = a.shift_f == 0 ? shift_into_tile<NS, 0, NPL, PLC>(cur, upc, d, w, sshift, smem_u32(p), sdump, n_own)
-                                      : shift_into_tile<NS, 1, NPL, PLC>(cur, upc, d, w, sshift, smem_u32(p), sdump, n_own);
+            int nNew = shift_into_tile<NS, F, NPL, PLC>(cur, upc, d, w, sshift, smem_u32(p), sdump, n_own);
             // in-band counts and flags, pair order: y3 = chunk 1 word 3, y5 = chunk 2 word 3, y7 = chunk 3 word 3
             float *fw = reinterpret_cast<float *>(p);
             const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
@@ -451,7 +449,7 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
                 if (NPL == 3) {
                     constexpr int PSI = PLC * 16;
                     const int placed_own = 2 * (n_own / PSI) + ((n_own % PSI) ? 1 : 0);
-                    dropped = shift_overflow3(a.shift_f, upc.x03, make_float2(upc.x47.x, upc.x47.y), upc.y03,
+                    dropped = shift_overflow3(F, upc.x03, make_float2(upc.x47.x, upc.x47.y), upc.y03,
                                               make_float2(upc.y47.x, upc.y47.y), upc.cnt, d, w, sshift, 2 * NPL - placed_own,
                                               nNew, fw + 2 * PLC * 4 + 3, owned, dout, &g, &a, t.X0 + i, t.Y0 + j);
                 } else dropped = nNew - 2 * NPL;
@@ -671,9 +669,15 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
 
     // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
     if (do_shift) {
-        if (ns4) shift_pass<4, TX, TY, NPL>(sm, t, g, a, dout, sdir, tid, ctr);
-        else if (!ns8) shift_pass<6, TX, TY, NPL>(sm, t, g, a, dout, sdir, tid, ctr);
-        else if (NPL == 4) shift_pass<8, TX, TY, NPL>(sm, t, g, a, dout, sdir, tid, ctr);
+        if (a.shift_f == 0) {
+            if (ns4) shift_pass<4, TX, TY, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (!ns8) shift_pass<6, TX, TY, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (NPL == 4) shift_pass<8, TX, TY, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+        } else {
+            if (ns4) shift_pass<4, TX, TY, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (!ns8) shift_pass<6, TX, TY, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (NPL == 4) shift_pass<8, TX, TY, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+        }
     }
 
     // ------------------------------------------------------------ owned tile -> HBM
