@@ -105,6 +105,13 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
     return v;
 }
 
+template <int BYTE_OFF>
+__device__ __forceinline__ void sts128(unsigned saddr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};"
+                 ::"r"(saddr), "n"(BYTE_OFF), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // in-band count: y7 when fewer than 8 disks (P3 = x6 x7 y6 y7), y5 when fewer than 6 (P2 = x4 x5 y4 y5)
 __device__ __forceinline__ int decode_cnt8(const float4 &p3) { return p3.y < kSentTest ? 8 : __float_as_int(p3.w); }
 __device__ __forceinline__ int decode_cnt6(const float4 &p2) { return p2.y < kSentTest ? 6 : __float_as_int(p2.w); }
@@ -121,9 +128,9 @@ __device__ __forceinline__ float2 pair2(float qx0, float qx1, float qy0, float q
 // smallest squared distance between the trial point (negated, in this cell's frame) and the
 // first NS slots of one staged cell; unused slots hold the sentinel
 template <int NS, int PLC>
-__device__ __forceinline__ float cell_min_d2(const float4 *cp, float npx, float npy)
+__device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float npy)
 {
-    const float4 p0 = cp[0], p1 = cp[PLC];
+    const float4 p0 = *reinterpret_cast<const float4 *>(cp), p1 = *reinterpret_cast<const float4 *>(cp + PLC * 16);
     // sign bit of y3 = "this cell holds 5 or more disks" (cell-local coordinates are positive):
     // only then are P2 (and P3) fetched, so quarter-warps whose 8 neighbour cells all hold <= 4
     // disks (61 % of them at phi = 0.70) spend no shared-memory wavefront on those planes
@@ -134,11 +141,11 @@ __device__ __forceinline__ float cell_min_d2(const float4 *cp, float npx, float 
     float m = fminf(fminf(a.x, a.y), fminf(b.x, b.y));
     if (NS >= 6) {
         if (more) {
-            const float4 p2 = cp[2 * PLC];
+            const float4 p2 = *reinterpret_cast<const float4 *>(cp + 2 * PLC * 16);
             const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
             m = fminf(m, fminf(c.x, c.y));
             if (NS == 8) {
-                const float4 p3 = cp[3 * PLC];
+                const float4 p3 = *reinterpret_cast<const float4 *>(cp + 3 * PLC * 16);
                 const float2 e = pair2(p3.x, p3.y, p3.z, p3.w, nx, ny);
                 m = fminf(m, fminf(e.x, e.y));
             }
@@ -273,14 +280,18 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     const int cps = g.cps;
     const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
     const int lo = k + 1;                       // cells closer than lo to the region edge are stale
+    // first active column / row of this colour in region coordinates: warp-uniform
     const int pi = ((int)((a.offmask >> (2 * k)) & 1u) - t.rx0) & 1;       // region-column parity of the active colour
     const int pj = ((int)((a.offmask >> (2 * k + 1)) & 1u) - (g.row0 + t.ry0)) & 1;
-    const int i = lo + ((pi - lo) & 1) + 2 * aq, j = lo + ((pj - lo) & 1) + 2 * bq;
+    const int i0 = lo + ((pi - lo) & 1), j0 = lo + ((pj - lo) & 1);
+    const int i = i0 + 2 * aq, j = j0 + 2 * bq;
     if (!(i < t.RX - lo && j < t.RY - lo)) return;
-    const int is = i + t.xs, par = is & 1;
-    float4 *pown = sm + j * PITCH + par * HB + (is >> 1);
-    const float4 *pL = sm + j * PITCH + (1 - par) * HB + ((is - 1) >> 1);      // left neighbour; right = pL + 1
-    const unsigned sown = smem_u32(pown);
+    // staged column is = i + xs = 2 aq + (i0 + xs): parity and half column split into a uniform and a lane part
+    const int isu = i0 + t.xs, par = isu & 1;
+    char *const cbase = reinterpret_cast<char *>(sm) + (2 * bq * PITCH + aq) * 16;
+    char *const cown = cbase + (j0 * PITCH + par * HB + (isu >> 1)) * 16;
+    const char *const cL = cbase + (j0 * PITCH + (1 - par) * HB + ((isu - 1) >> 1)) * 16;   // left neighbour; right = cL + 16
+    const unsigned sown = smem_u32(cown);
     const float4 p0 = lds128<0>(sown), p1 = lds128<PLC * 16>(sown), p2 = lds128<2 * PLC * 16>(sown);
     float4 p3 = make_float4(kSent, kSent, 0.f, 0.f);
     if (NS == 8) p3 = lds128<3 * PLC * 16>(sown);
@@ -300,11 +311,11 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const bool goL = px <= hw, goD = py <= hw;
         const float npxs = -__fadd_rn(px, goL ? w : -w);     // -(px - helper*w), subsweep.h:139-151
         const float npys = -__fadd_rn(py, goD ? w : -w);
-        const float4 *pH = pL + (goL ? 0 : 1);
-        const int dV = goD ? -PITCH : PITCH;
-        float m = cell_min_d2<NS, PLC>(pH, npxs, -py);
-        m = fminf(m, cell_min_d2<NS, PLC>(pown + dV, -px, npys));
-        m = fminf(m, cell_min_d2<NS, PLC>(pH + dV, npxs, npys));
+        const char *cH = cL + (goL ? 0 : 16);
+        const int dV = goD ? -PITCH * 16 : PITCH * 16;
+        float m = cell_min_d2<NS, PLC>(cH, npxs, -py);
+        m = fminf(m, cell_min_d2<NS, PLC>(cown + dV, -px, npys));
+        m = fminf(m, cell_min_d2<NS, PLC>(cH + dV, npxs, npys));
         return inb ? m : -1.0f;                 // out of the cell: rejected whatever the neighbours say
     };
 
@@ -330,6 +341,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         ox[s] = nx; oy[s] = ny;
     }
     // trials 0..3 move slot s mod cnt (subsweep.h:279-297), all register indices static
+    unsigned n_acc = 0;
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const bool cA = cnt > s;                            // slot == s
@@ -338,7 +350,6 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
         const float px = __fmaf_rn(signed_odd24(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
         const float py = __fmaf_rn(signed_odd24(rw[2 * s + 1]), dscale, y);
-        my_trials += owned ? 1u : 0u;
         float m = neighbours_min_d2(px, py);
         // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
         const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
@@ -360,7 +371,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         }
         // accept_move subsweep.h:194-217 (hard disks: accept iff in bounds and no overlap)
         const bool acc = !(m < sigma2);
-        my_acc += (acc && owned) ? 1u : 0u;
+        n_acc += acc ? 1u : 0u;
         if (s == 0) { ox[0] = acc ? px : ox[0]; oy[0] = acc ? py : oy[0]; }
         else {
             const bool w0 = acc & !cA & !cB, w1 = acc & cB, ws = acc & cA;
@@ -369,7 +380,9 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
             if (s == 3) { ox[1] = w1 ? px : ox[1]; oy[1] = w1 ? py : oy[1]; }
         }
     }
+    if (owned) { my_trials += 4u; my_acc += n_acc; }
     // cpy_D_sh_to_Disk subsweep.h:29-36 (shuffled order is written back, like the reference)
+    float4 *pown = reinterpret_cast<float4 *>(cown);
     pown[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
     pown[PLC] = make_float4(oy[0], oy[1], oy[2], cnt >= 5 ? -oy[3] : oy[3]);
     if (NS >= 6) pown[2 * PLC] = make_float4(ox[4], ox[5], oy[4], oy[5]);
