@@ -35,9 +35,9 @@ N_M, NMAX, SIGMA, CELL_W, SEED = 4, 8, 1.0, 2.0, 1234
 METRIC = "hard-disk trial moves/sec"
 UNIT = "moves/s"
 
-# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_v6_summary.txt):
+# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_v7_summary.txt):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 308.9e6 + 258.1e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 232.3e6 + 258.6e6}
 
 
 def algorithmic_bytes_per_sweep(n_particles, n_cells):
@@ -263,7 +263,7 @@ def main():
     if fast:
         # CUDA events bracket the sweep kernels of each pmc_sweep call (import / export excluded)
         ms_per_launch = kernel_ms / kernel_launches
-        kname = "sweep4_kernel<24|26,24,3> (one launch = one MC sweep: 4 colours + shiftCells)"
+        kname = "sweep4_kernel<24|26, 4 CTAs/SM, fast> (one launch = one MC sweep: 4 colours + shiftCells)"
     else:
         ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
         kname = "sweep_tile_kernel<4,26,32,320,2,*> (generic path)"
@@ -306,9 +306,44 @@ def main():
                "ms_per_step": e2e_ms / args.steps,
                "what": "pmc_run_host: H2D(r) + assign + sweeps + D2H(disk, n), pinned host buffers",
                "n_sum_check": int(n_host.to(torch.int64).sum().item())}
-    elif n_ranks > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "what": "not measured for slab runs (state stays on the GPUs between sweeps)"}
+    elif not args.no_e2e:
+        # slab runs: every rank's slab (caller layout, ghost rows included) starts and ends each step in
+        # pinned host memory; pmc_sweep runs on the device copy in between (ghost rows exchanged by NCCL)
+        disk_host = disk.cpu().pin_memory()
+        n_host = n.cpu().pin_memory()
+        mc.set_blocking(1)
+        for _ in range(2):
+            disk.copy_(disk_host, non_blocking=True); n.copy_(n_host, non_blocking=True)
+            mc.sweep(disk, n, sweep, S)
+            disk_host.copy_(disk, non_blocking=True); n_host.copy_(n, non_blocking=True)
+            sweep += S
+        torch.cuda.synchronize()
+        mc.reset_counters()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            disk.copy_(disk_host, non_blocking=True); n.copy_(n_host, non_blocking=True)
+            mc.sweep(disk, n, sweep, S)
+            disk_host.copy_(disk, non_blocking=True); n_host.copy_(n, non_blocking=True)
+            sweep += S
+        f1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dist.barrier()
+        ce = mc.counters()
+        et = torch.tensor([max(f0.elapsed_time(f1), wall * 1e3)], dtype=torch.float64, device="cuda")
+        etr = torch.tensor([ce["trials"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        dist.all_reduce(etr, op=dist.ReduceOp.SUM)
+        e2e_ms = float(et.item())
+        nbytes = int(disk_host.numel() * 4 + n_host.numel() * 2) * n_ranks
+        e2e = {"value": float(etr.item()) / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": e2e_ms / args.steps,
+               "what": "per rank: H2D(slab disk, n) + pmc_sweep (NCCL ghost rows) + D2H(slab disk, n), pinned host buffers; max over ranks"}
 
     cpu = None
     if rank == 0 and n_ranks == 1 and not args.no_cpu_baseline:

@@ -53,7 +53,7 @@ int oracle_make_geom(int64_t n_particles, float phi, float sigma_d, float cell_w
     g->sigma = sigma_d;
     g->sigma2 = sigma_d * sigma_d;
     g->delta = move_delta;
-    g->dscale = move_delta * 5.9604644775390625e-08f; /* 2^-24, exact scaling */
+    g->dscale = move_delta * 1.1920928955078125e-07f; /* 2^-23, exact scaling */
     g->seed = seed;
     return 0;
 }
@@ -241,13 +241,11 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
         uint32_t ra = words[2 * s], rb = words[2 * s + 1];
         int slot = s % cnt;                               /* i = (i+1) mod atom_counts, subsweep.h:291-296 */
         /* make_move subsweep.h:60-71; proposal = uniform in the square:
-         * +-(odd integer < 2^24) times delta*2^-24: an exactly symmetric set of 2^24 values per
-         * axis; sign = top random bit, magnitude = next 23 bits; one fused rounding per axis */
-        uint32_t ta = ra >> 8, tb = rb >> 8;
-        float fmx = (float)(int)(2u * (ta & 0x7FFFFFu) + 1u);
-        float fmy = (float)(int)(2u * (tb & 0x7FFFFFu) + 1u);
-        if (ta & 0x800000u) fmx = -fmx;
-        if (tb & 0x800000u) fmy = -fmy;
+         * (odd integer, |.| < 2^23) times delta*2^-23: an exactly symmetric set of 2^23 values per
+         * axis, 2k + 1 with k = (top 23 random bits) - 2^22; one fused rounding per axis.  (The
+         * low 8 bits of the words feed the shuffle above; bit 8 is unused.) */
+        float fmx = fmaf((float)(int)(ra >> 9) - 4194304.0f, 2.0f, 1.0f);
+        float fmy = fmaf((float)(int)(rb >> 9) - 4194304.0f, 2.0f, 1.0f);
         float px = fmaf(fmx, g->dscale, X[slot]);
         float py = fmaf(fmy, g->dscale, Y[slot]);
         (*trials)++;

@@ -143,7 +143,7 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     g.half_L = g.L / 2.0f;
     g.sigma = p.sigma_d;
     g.sigma2 = p.sigma_d * p.sigma_d;
-    g.dscale = p.move_delta * 5.9604644775390625e-08f;
+    g.dscale = p.move_delta * 1.1920928955078125e-07f;     // 2^-23
     g.n_M = p.n_M;
     g.seed_lo = (unsigned)p.seed;
     g.seed_hi = (unsigned)(p.seed >> 32);

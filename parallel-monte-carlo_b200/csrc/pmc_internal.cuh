@@ -21,7 +21,7 @@ struct DevGeom {
     float w;
     float sigma;
     float sigma2;
-    float dscale;           // move_delta * 2^-24
+    float dscale;           // move_delta * 2^-23
     float L;
     float half_L;
     double L_box;

@@ -149,13 +149,14 @@ __device__ __forceinline__ float cell_min_d2(const float4 *cellp, float npx, flo
     return fminf(fminf(fminf(a.x, a.y), fminf(b.x, b.y)), fminf(fminf(c.x, c.y), fminf(e.x, e.y)));
 }
 
-// +-(odd integer < 2^24) as a float without I2F (which runs on the quarter-rate XU pipe):
-// 0x4B800000 | m23 is the float 2^24 + 2*m23; subtracting 2^24 - 1 is exact.
-__device__ __forceinline__ float signed_odd24(uint32_t r)
+// odd integer 2k + 1, k = (top 23 bits of r) - 2^22: symmetric, exact in binary32, without I2F
+__device__ __forceinline__ float signed_odd23(uint32_t r)
 {
-    const float a = __uint_as_float(((r >> 8) & 0x7FFFFFu) | 0x4B800000u);
-    const float mag = __fadd_rn(a, -16777215.0f);
-    return __uint_as_float(__float_as_uint(mag) | (r & 0x80000000u));
+    // 2^23 + (r >> 9) as a float straight from the integer multiplier (no shift / mask on the ALU pipe)
+    uint32_t tb;
+    asm("mad.hi.u32 %0, %1, 8388608, 1258291200;" : "=r"(tb) : "r"(r));     // (r * 2^23 >> 32) + 0x4B000000
+    const float k = __fadd_rn(__uint_as_float(tb), -12582912.0f);             // (r >> 9) - 2^22, exact
+    return __fmaf_rn(k, 2.0f, 1.0f);
 }
 
 // d2 of the trial point against two slots held in registers
@@ -452,8 +453,8 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
                     const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
                     const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-                    const float px = __fmaf_rn(signed_odd24(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
-                    const float py = __fmaf_rn(signed_odd24(rw[2 * s + 1]), dscale, y);
+                    const float px = __fmaf_rn(signed_odd23(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
+                    const float py = __fmaf_rn(signed_odd23(rw[2 * s + 1]), dscale, y);
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
@@ -515,8 +516,8 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     float *fx = slot_ptr(it), *fy = fx + 2 * PL * 4;
                     it = (it + 1 >= cnt) ? 0 : it + 1;
                     const float x = *fx, y = *fy;
-                    const float px = __fmaf_rn(signed_odd24(ra), dscale, x);
-                    const float py = __fmaf_rn(signed_odd24(rb), dscale, y);
+                    const float px = __fmaf_rn(signed_odd23(ra), dscale, x);
+                    const float py = __fmaf_rn(signed_odd23(rb), dscale, y);
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     if (m >= 0.0f) {

@@ -154,12 +154,14 @@ __device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float np
     return m;
 }
 
-// +-(odd integer < 2^24) as a float without I2F: 0x4B800000 | m23 is the float 2^24 + 2*m23
-__device__ __forceinline__ float signed_odd24(uint32_t r)
+// odd integer 2k + 1, k = (top 23 bits of r) - 2^22: symmetric, exact in binary32, without I2F
+__device__ __forceinline__ float signed_odd23(uint32_t r)
 {
-    const float a = __uint_as_float(((r >> 8) & 0x7FFFFFu) | 0x4B800000u);
-    const float mag = __fadd_rn(a, -16777215.0f);
-    return __uint_as_float(__float_as_uint(mag) | (r & 0x80000000u));
+    // 2^23 + (r >> 9) as a float straight from the integer multiplier (no shift / mask on the ALU pipe)
+    uint32_t tb;
+    asm("mad.hi.u32 %0, %1, 8388608, 1258291200;" : "=r"(tb) : "r"(r));     // (r * 2^23 >> 32) + 0x4B000000
+    const float k = __fadd_rn(__uint_as_float(tb), -12582912.0f);             // (r >> 9) - 2^22, exact
+    return __fmaf_rn(k, 2.0f, 1.0f);
 }
 
 // V2 shiftCells.h:23-112 for one destination cell.  The result is scattered in place into the
@@ -304,10 +306,10 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     const uint32_t cell_id = (uint32_t)gy * (uint32_t)cps + (uint32_t)gx;
 
     // neighbour part of one trial: smallest d2 against the 3 neighbour cells that can hold a
-    // disk closer than sigma (w >= 2 sigma), or -1 when the proposal leaves the cell
+    // disk closer than sigma (w >= 2 sigma); inb = the proposal stays inside the cell
     // (out_of_bound subsweep.h:73-88)
-    auto neighbours_min_d2 = [&](const float px, const float py) -> float {
-        const bool inb = px > 0.0f && px <= w && py > 0.0f && py <= w;
+    auto neighbours_min_d2 = [&](const float px, const float py, bool &inb) -> float {
+        inb = px > 0.0f && px <= w && py > 0.0f && py <= w;
         const bool goL = px <= hw, goD = py <= hw;
         const float npxs = -__fadd_rn(px, goL ? w : -w);     // -(px - helper*w), subsweep.h:139-151
         const float npys = -__fadd_rn(py, goD ? w : -w);
@@ -316,7 +318,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         float m = cell_min_d2<NS, PLC>(cH, npxs, -py);
         m = fminf(m, cell_min_d2<NS, PLC>(cown + dV, -px, npys));
         m = fminf(m, cell_min_d2<NS, PLC>(cH + dV, npxs, npys));
-        return inb ? m : -1.0f;                 // out of the cell: rejected whatever the neighbours say
+        return m;
     };
 
     float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
@@ -348,9 +350,10 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
         const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
         const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-        const float px = __fmaf_rn(signed_odd24(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
-        const float py = __fmaf_rn(signed_odd24(rw[2 * s + 1]), dscale, y);
-        float m = neighbours_min_d2(px, py);
+        const float px = __fmaf_rn(signed_odd23(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
+        const float py = __fmaf_rn(signed_odd23(rw[2 * s + 1]), dscale, y);
+        bool inb;
+        float m = neighbours_min_d2(px, py, inb);
         // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
         const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
         float2 d01 = pair2(ox[0], ox[1], oy[0], oy[1], npx, npy);
@@ -370,7 +373,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
             m = fminf(m, fminf(d67.x, d67.y));
         }
         // accept_move subsweep.h:194-217 (hard disks: accept iff in bounds and no overlap)
-        const bool acc = !(m < sigma2);
+        const bool acc = inb && !(m < sigma2);      // out of the cell: rejected whatever the neighbours say
         n_acc += acc ? 1u : 0u;
         if (s == 0) { ox[0] = acc ? px : ox[0]; oy[0] = acc ? py : oy[0]; }
         else {
