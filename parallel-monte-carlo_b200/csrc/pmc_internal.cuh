@@ -53,6 +53,11 @@ struct SweepArgs {
     const unsigned *flag_in;    // flags of the state being read, valid where == epoch_in
     unsigned *flag_out;         // flags of the state being written, stamped with epoch_out
     unsigned epoch_in, epoch_out;
+    // fused fast path: how far from the edge of the staged region colour k still has to be computed,
+    // per axis, 4 bits per colour (1..4).  A halo cell of colour k at distance d from the owned cells
+    // matters only if d later colours alternate the parity along that axis (each step towards the owned
+    // cells crosses one column / row), so lo(k) = 5 - (longest alternating subsequence starting at k).
+    unsigned lo_x, lo_y;
     int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
                             // 8 treat every tile as crowded, 16 never use the 4-slot instantiation
 };

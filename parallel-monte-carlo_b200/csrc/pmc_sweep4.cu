@@ -281,13 +281,14 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
     const int cps = g.cps;
     const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
-    const int lo = k + 1;                       // cells closer than lo to the region edge are stale
+    // cells closer than lo to the region edge are stale or irrelevant (SweepArgs::lo_x): k + 1 at most
+    const int lox = (int)((a.lo_x >> (4 * k)) & 15u), loy = (int)((a.lo_y >> (4 * k)) & 15u);
     // first active column / row of this colour in region coordinates: warp-uniform
     const int pi = ((int)((a.offmask >> (2 * k)) & 1u) - t.rx0) & 1;       // region-column parity of the active colour
     const int pj = ((int)((a.offmask >> (2 * k + 1)) & 1u) - (g.row0 + t.ry0)) & 1;
-    const int i0 = lo + ((pi - lo) & 1), j0 = lo + ((pj - lo) & 1);
+    const int i0 = lox + ((pi - lox) & 1), j0 = loy + ((pj - loy) & 1);
     const int i = i0 + 2 * aq, j = j0 + 2 * bq;
-    if (!(i < t.RX - lo && j < t.RY - lo)) return;
+    if (!(i < t.RX - lox && j < t.RY - loy)) return;
     // staged column is = i + xs = 2 aq + (i0 + xs): parity and half column split into a uniform and a lane part
     const int isu = i0 + t.xs, par = isu & 1;
     char *const cbase = reinterpret_cast<char *>(sm) + (2 * bq * PITCH + aq) * 16;
