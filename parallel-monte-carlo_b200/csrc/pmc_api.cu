@@ -490,30 +490,15 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         a.shift_on = 1; a.shift_f = f; a.shift_d = d;
         a.dbg_skip = dbg;
         a.prefetch_ahead = pf_ahead;
-        for (int k = 3; k >= 0; k--) {
-            // longest parity-alternating subsequence of the colour order that starts at colour k
-            int lx = 1, ly = 1;
-            for (int m = k + 1; m < 4; m++) {
-                const int cx = (int)((a.lo_x >> (4 * m)) & 15u), cy = (int)((a.lo_y >> (4 * m)) & 15u);     // = las(m) for now
-                if (a.offx[m] != a.offx[k] && cx + 1 > lx) lx = cx + 1;
-                if (a.offy[m] != a.offy[k] && cy + 1 > ly) ly = cy + 1;
-            }
-            a.lo_x |= (unsigned)lx << (4 * k); a.lo_y |= (unsigned)ly << (4 * k);
-        }
-        if (dbg & 64) { a.lo_x = 0x1234u; a.lo_y = 0x1234u; }     // las = 4, 3, 2, 1: the full halo for every colour
-        for (int k = 0; k < 4; k++) {                               // las -> lo = 5 - las
-            const unsigned lx = 5u - ((a.lo_x >> (4 * k)) & 15u), ly = 5u - ((a.lo_y >> (4 * k)) & 15u);
-            a.lo_x = (a.lo_x & ~(15u << (4 * k))) | (lx << (4 * k));
-            a.lo_y = (a.lo_y & ~(15u << (4 * k))) | (ly << (4 * k));
-        }
+        pmc4_plan_sweep(a, dbg & 64);               // tile extent and halo from the colour order (64: always the full halo)
         h->v4_epoch[cur ^ 1] = next_epoch();
         a.flag_in = h->v4_flags[cur]; a.epoch_in = h->v4_epoch[cur];
         a.flag_out = h->v4_flags[cur ^ 1]; a.epoch_out = h->v4_epoch[cur ^ 1];
         const void *tm = h->v4_tmap[cur][0], *tmh = h->v4_tmap[cur][1];
         float4 *dst = h->v4_buf[cur ^ 1];
-        const int gy = pmc4_tile_rows(h->g4), ty = pmc4_tile_y();
+        const int gy = pmc4_tile_rows(h->g4, a);
         // tile rows that hold one of the kMY owned rows next to a slab face
-        const int top0 = (h->g4.rows - kMY) / ty;
+        const int top0 = (h->g4.rows - kMY) / a.ty;
         if (h->p.n_ranks > 1 && overlap && top0 > 1 && top0 < gy) {
             // boundary tile rows first (their boxes hold ghost rows, which carry no crowded-cell flags: the
             // 4-plane kernel); their ghost-row exchange overlaps the interior rows (the fast kernel)

@@ -53,10 +53,10 @@ struct SweepArgs {
     const unsigned *flag_in;    // flags of the state being read, valid where == epoch_in
     unsigned *flag_out;         // flags of the state being written, stamped with epoch_out
     unsigned epoch_in, epoch_out;
-    // fused fast path: how far from the edge of the staged region colour k still has to be computed,
-    // per axis, 4 bits per colour (1..4).  A halo cell of colour k at distance d from the owned cells
-    // matters only if d later colours alternate the parity along that axis (each step towards the owned
-    // cells crosses one column / row), so lo(k) = 5 - (longest alternating subsequence starting at k).
+    // fused fast path, filled by pmc4_plan_sweep from the colour order and the shift: owned extent of a
+    // tile, halo per axis, and how far from the edge of the staged region colour k still has to be
+    // computed (4 bits per colour, >= 1)
+    int tx, ty, hx, hy;
     unsigned lo_x, lo_y;
     int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
                             // 8 treat every tile as crowded, 16 never use the 4-slot instantiation
@@ -92,19 +92,17 @@ struct Geom4 {
     int try_ns4;                // mean occupancy is low: worth scanning for tiles whose cells all hold <= 4 disks
     unsigned pk0[10], pk1[10];  // Philox round keys seed + r * (0x9E3779B9, 0xBB67AE85): constant-bank operands
 };
-int pmc4_tile_x();
-int pmc4_tile_y();
+void pmc4_plan_sweep(SweepArgs &a, int full_halo);
+int pmc4_tile_rows(const Geom4 &g, const SweepArgs &a);
 void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS, int *FW, int *FH);
 int pmc4_make_tensor_map(void *tmap_out128, const float4 *base, const Geom4 &g, int half);
 cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out,
                                unsigned *flags, unsigned epoch, cudaStream_t st);
 cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, float4 *disk, int16_t *n, cudaStream_t st);
-// tile rows [by0, by0 + nby) of one sweep (nby <= 0: all rows), optional second band [by1, by1 + nby1)
-// in the same launch; fast = 1: the 3-plane / 4-CTA kernel (boxes must not touch slab ghost rows)
+// tile rows [by0, by0 + nby) of one planned sweep (nby <= 0: all rows), optional second band
+// [by1, by1 + nby1) in the same launch; fast = 1: the 3-plane / 4-CTA kernel (boxes must not touch slab ghost rows)
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a,
                               Counters *ctr, cudaStream_t st, int fast, int by0 = 0, int nby = 0, int by1 = 0, int nby1 = 0);
-int pmc4_tile_rows(const Geom4 &g);
-int pmc4_tile_count(const Geom4 &g);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ Philox4x32-10

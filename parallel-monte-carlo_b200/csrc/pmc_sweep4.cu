@@ -42,24 +42,27 @@ constexpr float kSentTest = 1.0e17f;      // x < kSentTest <=> slot in use
 constexpr int kNT = 256;                  // threads per CTA of every kernel in this file
 constexpr int kFB = 3;                    // log2 of the flag block edge (8 x 8 internal cells per flag word)
 
-template <int TX, int TY>
-struct Tile4 {
-    static constexpr int H = 4;                                  // halo: one cell per colour
-    static constexpr int HB = ((TX + 10) / 2 + 1) / 2 * 2;       // staged chunks per parity row (even)
+// The staged box: 36 columns (18 per parity) x SYB rows of cells per plane, the same for every
+// tiling.  How much of it is owned is decided per sweep (SweepArgs::tx, ty, hx, hy): the halo a sweep
+// needs depends on its colour order, and a shallower halo leaves room for a larger tile.
+template <int SYB_>
+struct Box4 {
+    static constexpr int HB = 18;                                // staged chunks per parity row
     static constexpr int PITCH = 2 * HB;                         // chunks per staged row
-    static constexpr int SYB = TY + 2 * H + 1;                   // staged rows
+    static constexpr int SYB = SYB_;                             // staged rows
     static constexpr int PLB = PITCH * SYB;                      // chunks the TMA box brings per plane
     static constexpr int PLC = (PLB + 7) / 8 * 8;                // plane stride (128-byte aligned)
-    // active cells per colour and row: at most 16 (half a warp, two conflict-free quarter-warps).
-    // TX = 24 always fits; TX = 26 fits when the tile carries no extra column (shift along y).
-    static constexpr int NAX = 16, NAY = (TY + 2 * H) / 2;
-    static constexpr int THREADS = NAX * NAY;
+    // active cells per colour: at most 16 per row (half a warp, two conflict-free quarter-warps)
+    // in at most 16 rows: one thread each
+    static constexpr int NAX = 16;
     static constexpr size_t PLANE_BYTES = (size_t)PLC * 16;
-    static_assert(TX % 2 == 0 && TY % 2 == 0 && TX + 2 * H <= 2 * NAX + 2, "tile shape");
     static_assert(4 * HB <= 256 && SYB <= 256, "TMA box extents");
-    static_assert(THREADS <= kNT, "one thread per active cell of a colour");
-    static_assert(PLC > PLB, "the mbarrier lives in the padding behind plane 0");
+    static_assert((SYB - 1) / 2 <= kNT / NAX, "one thread per active cell of a colour");
+    static_assert((PLC - PLB) * 16 >= 32, "padding behind the planes: mbarrier (plane 0), dump word (plane 1)");
 };
+constexpr int kSYB = 33, kSYBH = 21;      // rows of the full box; of the half-height box of a crowded tile
+using BoxF = Box4<kSYB>;
+using BoxH = Box4<kSYBH>;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -270,14 +273,14 @@ struct TileCtx {
     int ox0, oy0;           // region coordinates of the owned tile's corner
     int nox, noy;           // owned extent after clipping at the box / slab edge
     int X0, Y0;             // internal array coordinates of region (0, 0)
+    int tx, ty;             // nominal owned extent of this tiling
 };
 
 // ---- one colour: one thread per active cell (subsweep.h:242-245), own cell in registers
-template <int NS, int TX, int TY>
+template <int NS, typename TL>
 __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
                                             int k, int aq, int bq, unsigned &my_trials, unsigned &my_acc)
 {
-    using TL = Tile4<TX, TY>;
     constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
     const int cps = g.cps;
     const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
@@ -394,11 +397,11 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
 }
 
 // ---- shiftCells(f, d) of this sweep for the owned cells, in place (pair order out)
-template <int NS, int TX, int TY, int NPL, int F>
+template <int NS, typename TL, int NPL, int F>
 __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
                                            float4 *__restrict__ dout, int sdir, int tid, Counters *ctr)
 {
-    using TL = Tile4<TX, TY>;
+    const int TX = t.tx, TY = t.ty;
     constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
     const float d = a.shift_d, w = g.w;
     const float sshift = __fmul_rn(w, (float)sdir);                 // shiftCells.h:84-86
@@ -407,8 +410,10 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
     // last cell and the raw cell after the strip (first cell of the next strip, or the extra
     // upstream row / column); cell u is then rewritten with raw u as `own` and raw u+1, still
     // in registers, as `up`.  Only two cells are ever live in registers.
-    constexpr int SEG1 = kNT / TX, K1 = (TY + SEG1 - 1) / SEG1;     // f = 1: column strips of K1 rows
-    constexpr int SEG0 = kNT / TY < 8 ? kNT / TY : 8, K0 = (TX + SEG0 - 1) / SEG0;   // f = 0: row strips of K0 columns
+    const int SEG1 = kNT / TX, K1 = (TY + SEG1 - 1) / SEG1;         // f = 1: column strips of K1 rows
+    constexpr int SEG0 = 8;                                         // f = 0: row strips of K0 columns (TY <= 32 rows of 8 threads)
+    const int K0 = (TX + SEG0 - 1) / SEG0;
+    constexpr int KMAX = 4;                                         // TX <= 32, TY <= 32: 8 strips of at most 4 cells
     int i0, j0, len;
     const int di = F == 0 ? sdir : 0, dj = F == 0 ? 0 : sdir;
     if (F == 1) {
@@ -447,7 +452,6 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
         load_cell(i0 + len * di, j0 + len * dj, upc);
     }
     __syncthreads();
-    constexpr int KMAX = F == 0 ? K0 : K1;
 #pragma unroll
     for (int v = 0; v < KMAX; v++) {
         const int u = len - 1 - v;
@@ -497,17 +501,17 @@ __device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const G
 // parity, plane pair), rows strided: a warp stores runs of TX/2 consecutive float4.  After the
 // shift the staged cells are in pair order and are converted to P0..P3 here: the thread of plane
 // pair 0 reads chunks 0, 1 and writes P0, P1; the thread of pair 1 reads chunks 2 (, 3), writes P2, P3.
-template <int TX, int TY, int NPL>
+template <typename TL, int NPL>
 __device__ __forceinline__ void store_pass(const float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
-                                           float4 *__restrict__ dout, bool pair_order, int tbx, int tby, int tid)
+                                           float4 *__restrict__ dout, bool pair_order, int col0, int row0, int tid)
 {
-    using TL = Tile4<TX, TY>;
-    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC, HX = TX / 2;
-    constexpr int RSTEP = kNT / (4 * HX);                          // threads beyond RSTEP * 4 * HX do not store
+    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
+    const int HX = t.tx / 2;
+    const int RSTEP = kNT / (4 * HX);                              // threads beyond RSTEP * 4 * HX do not store
     const int cps = g.cps;
     const int h = tid % HX, pr = (tid / HX) & 1, pp = (tid / (2 * HX)) & 1, rg = tid / (4 * HX);
     const int ox = 2 * h + pr;                                      // owned column (parity == internal column parity)
-    const int ux = tbx * TX + ox, uy0 = tby * TY;
+    const int ux = col0 + ox, uy0 = row0;
     if (!(ox < t.nox && rg < RSTEP)) return;
     const int is = t.ox0 + ox + t.xs;
     unsigned src = smem_u32(sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH + 2 * pp * PLC);
@@ -569,20 +573,21 @@ __device__ __forceinline__ void store_pass(const float4 *sm, const TileCtx &t, c
     }
 }
 
-// ---- one tile of one sweep: stage, 4 colours, shiftCells, store.  tbx / tby = tile column / row
-// in the TX x TY tiling; `phase` = parity of the mbarrier phase this staging completes.
+// ---- one tile of one sweep: stage, 4 colours, shiftCells, store.  (col0, row0) = first owned column /
+// owned-relative row, tx x ty = nominal owned extent (a.tx x a.ty, or half the rows for a crowded tile);
+// `phase` = parity of the mbarrier phase this staging completes.
 // NPL = 3 is the fast path: it first looks up the crowded-cell flags of the blocks its box
 // touches and returns true, having done nothing, when one is set.
-template <int TX, int TY, int NPL>
+template <typename TL, int NPL>
 __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *__restrict__ dout, const Geom4 &g,
-                                             const SweepArgs &a, Counters *ctr, int tbx, int tby,
+                                             const SweepArgs &a, Counters *ctr, int col0, int row0, int tx, int ty,
                                              float4 *sm, uint64_t *mbar, unsigned phase, bool prefetch,
                                              unsigned &my_trials, unsigned &my_acc)
 {
-    using TL = Tile4<TX, TY>;
-    constexpr int H = TL::H, PLC = TL::PLC, NAX = TL::NAX;
+    constexpr int PLC = TL::PLC, NAX = TL::NAX;
     const int tid = threadIdx.x;
     const int cps = g.cps;
+    const int HX = a.hx, HY = a.hy;                 // halo this sweep's colour order needs, per axis (2..4)
 
     // this sweep's grid shift: the tile carries one extra row / column on the upstream side
     const bool do_shift = a.shift_on && !(a.dbg_skip & 2);
@@ -590,13 +595,14 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     const int exl = (do_shift && a.shift_f == 0 && sdir < 0), exh = (do_shift && a.shift_f == 0 && sdir > 0);
     const int eyl = (do_shift && a.shift_f == 1 && sdir < 0), eyh = (do_shift && a.shift_f == 1 && sdir > 0);
     TileCtx t;
-    t.RX = TX + 2 * H + exl + exh; t.RY = TY + 2 * H + eyl + eyh;
-    t.rx0 = tbx * TX - H - exl;
-    t.ry0 = tby * TY - H - eyl;
+    t.tx = tx; t.ty = ty;
+    t.RX = tx + 2 * HX + exl + exh; t.RY = ty + 2 * HY + eyl + eyh;
+    t.rx0 = col0 - HX - exl;
+    t.ry0 = row0 - HY - eyl;
     t.X0 = t.rx0 + kMX; t.Y0 = t.ry0 + kMY;         // region (0, 0) in internal array coordinates (>= 0)
     t.xs = t.X0 & 1;
-    t.ox0 = H + exl; t.oy0 = H + eyl;
-    t.nox = min(TX, cps - tbx * TX); t.noy = min(TY, g.rows - tby * TY);
+    t.ox0 = HX + exl; t.oy0 = HY + eyl;
+    t.nox = min(tx, cps - col0); t.noy = min(ty, g.rows - row0);
     const int Xb0 = t.X0 - t.xs;                    // first column of the staged box
 
     // ------------------------------------------------------------ stage the tile: one TMA box per plane
@@ -610,7 +616,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
             if (nb < (int)(gridDim.x * gridDim.y)) {
                 const int gr2 = nb / gridDim.x, bx2 = nb - gr2 * gridDim.x;
                 const int by2 = gr2 < a.by_n1 ? gr2 + a.by_off : gr2 - a.by_n1 + a.by_off2;
-                const int X2 = bx2 * TX - H - exl + kMX, Y2 = by2 * TY - H - eyl + kMY;
+                const int X2 = bx2 * a.tx - HX - exl + kMX, Y2 = by2 * a.ty - HY - eyl + kMY;
 #pragma unroll
                 for (int p = 0; p < NPL; p++) tma_prefetch_4d(tmap_p, 4 * ((X2 - (X2 & 1)) >> 1), 0, p, Y2);
             }
@@ -666,19 +672,19 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
         if (ns4) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                colour_pass<4, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                colour_pass<4, TL>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
                 __syncthreads();
             }
         } else if (!ns8) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                colour_pass<6, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                colour_pass<6, TL>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
                 __syncthreads();
             }
         } else if (NPL == 4) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                colour_pass<8, TX, TY>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                colour_pass<8, TL>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
                 __syncthreads();
             }
         }
@@ -687,18 +693,18 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
     if (do_shift) {
         if (a.shift_f == 0) {
-            if (ns4) shift_pass<4, TX, TY, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (!ns8) shift_pass<6, TX, TY, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (NPL == 4) shift_pass<8, TX, TY, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+            if (ns4) shift_pass<4, TL, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (!ns8) shift_pass<6, TL, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (NPL == 4) shift_pass<8, TL, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
         } else {
-            if (ns4) shift_pass<4, TX, TY, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (!ns8) shift_pass<6, TX, TY, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (NPL == 4) shift_pass<8, TX, TY, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+            if (ns4) shift_pass<4, TL, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (!ns8) shift_pass<6, TL, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+            else if (NPL == 4) shift_pass<8, TL, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
         }
     }
 
     // ------------------------------------------------------------ owned tile -> HBM
-    if (!(a.dbg_skip & 4)) store_pass<TX, TY, NPL>(sm, t, g, a, dout, do_shift, tbx, tby, tid);
+    if (!(a.dbg_skip & 4)) store_pass<TL, NPL>(sm, t, g, a, dout, do_shift, col0, row0, tid);
     return false;
 }
 
@@ -713,18 +719,14 @@ __device__ __forceinline__ void flush_counters(Counters *ctr, unsigned my_trials
     }
 }
 
-constexpr int kTY = 24, kTYS = 12;      // tile height; height of the two half tiles a crowded tile is split into
-
 // ---- crowded tile (a staged cell holds 7 or 8 disks): all four planes, half the rows at a time, in the
 // shared memory of the fast tile.  Rare, and deliberately NOT inlined: the fast path keeps its own
 // register allocation (64 registers without spills).  Returns (trials << 32) | accepted of this thread.
-template <int TX>
 __device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_half, float4 *dout, const Geom4 *gp,
-                                                        const SweepArgs *ap, Counters *ctr, int tbx, int tby,
+                                                        const SweepArgs *ap, Counters *ctr, int col0, int row0,
                                                         float4 *sm, uint64_t *mbar_fast)
 {
-    using TS = Tile4<TX, kTYS>;
-    uint64_t *mbar2 = reinterpret_cast<uint64_t *>(sm + TS::PLB);
+    uint64_t *mbar2 = reinterpret_cast<uint64_t *>(sm + BoxH::PLB);
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar_fast)) : "memory");
@@ -733,43 +735,46 @@ __device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_
     }
     __syncthreads();
     unsigned my_trials = 0, my_acc = 0;
+    // rows a half-height box can own: its kSYBH rows hold the halo on both sides and the upstream row
+    const int tyh = (kSYBH - 1 - 2 * ap->hy) & ~1;
+    unsigned phase = 0;
 #pragma unroll 1
-    for (int half = 0; half < kTY / kTYS; half++) {
-        const int tbys = tby * (kTY / kTYS) + half;
-        if (tbys * kTYS < gp->rows)
-            process_tile<TX, kTYS, 4>(tmap_half, dout, *gp, *ap, ctr, tbx, tbys, sm, mbar2, (unsigned)(half & 1), false,
-                                      my_trials, my_acc);
+    for (int r = 0; r < ap->ty; r += tyh) {
+        const int ty = min(tyh, ap->ty - r);
+        if (row0 + r < gp->rows) {
+            process_tile<BoxH, 4>(tmap_half, dout, *gp, *ap, ctr, col0, row0 + r, ap->tx, ty, sm, mbar2, phase, false,
+                                  my_trials, my_acc);
+            phase ^= 1u;
+        }
         __syncthreads();                        // every thread is done with the tile before the next box lands on it
         if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     return ((unsigned long long)my_trials << 32) | my_acc;
 }
 
-// ---- one launch = one sweep.  FAST: 3 planes staged, 4 CTAs per SM, crowded tiles re-done as two
-// half tiles with 4 planes in the same shared memory.  !FAST: 4 planes, 3 CTAs per SM, no flag
+// ---- one launch = one sweep.  FAST: 3 planes staged, 4 CTAs per SM, crowded tiles re-done in two or
+// three 4-plane pieces in the same shared memory.  !FAST: 4 planes, 3 CTAs per SM, no flag
 // lookup (slab boundary rows, whose ghost rows carry no flags).
-template <int TX, int MINB, bool FAST>
+template <int MINB, bool FAST>
 __global__ void __launch_bounds__(kNT, MINB)
 sweep4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
               float4 *__restrict__ dout, const __grid_constant__ Geom4 g, const __grid_constant__ SweepArgs a, Counters *ctr)
 {
-    using TL = Tile4<TX, kTY>;
-    using TS = Tile4<TX, kTYS>;
-    static_assert(4 * TS::PLANE_BYTES <= 3 * TL::PLANE_BYTES, "the half tiles reuse the fast tile's shared memory");
+    static_assert(4 * BoxH::PLANE_BYTES <= 3 * BoxF::PLANE_BYTES, "the half-height boxes reuse the fast tile's shared memory");
     extern __shared__ __align__(128) float4 sm[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + TL::PLB);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + BoxF::PLB);
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // tile row (a launch may cover one or two bands of rows)
     const int tby = (int)blockIdx.y < a.by_n1 ? (int)blockIdx.y + a.by_off : (int)blockIdx.y - a.by_n1 + a.by_off2;
-    const int tbx = (int)blockIdx.x;
+    const int col0 = (int)blockIdx.x * a.tx, row0 = tby * a.ty;
     unsigned my_trials = 0, my_acc = 0;
     if (!FAST) {
-        process_tile<TX, kTY, 4>(&tmap, dout, g, a, ctr, tbx, tby, sm, mbar, 0u, true, my_trials, my_acc);
-    } else if (process_tile<TX, kTY, 3>(&tmap, dout, g, a, ctr, tbx, tby, sm, mbar, 0u, true, my_trials, my_acc)) {
-        const unsigned long long r = crowded_tile<TX>(&tmap_half, dout, &g, &a, ctr, tbx, tby, sm, mbar);
+        process_tile<BoxF, 4>(&tmap, dout, g, a, ctr, col0, row0, a.tx, a.ty, sm, mbar, 0u, true, my_trials, my_acc);
+    } else if (process_tile<BoxF, 3>(&tmap, dout, g, a, ctr, col0, row0, a.tx, a.ty, sm, mbar, 0u, true, my_trials, my_acc)) {
+        const unsigned long long r = crowded_tile(&tmap_half, dout, &g, &a, ctr, col0, row0, sm, mbar);
         my_trials += (unsigned)(r >> 32); my_acc += (unsigned)r;
     }
     flush_counters(ctr, my_trials, my_acc);
@@ -865,20 +870,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-// The tiling: 24 x 24 owned cells; sweeps that do not shift along x use 26-column tiles (16, 15,
-// 14, 13 active cells per half-warp instead of 15, 14, 13, 12); the staged box is the same, so is
-// the tensor map.  A second map with the half-height box serves the crowded tiles.
-constexpr int kTXN = 24, kTXW = 26;
-static_assert(Tile4<kTXN, kTY>::HB == Tile4<kTXW, kTY>::HB && Tile4<kTXN, kTYS>::HB == Tile4<kTXW, kTYS>::HB,
-              "one TMA box for both tile widths");
-
-template <int TX, int MINB, bool FAST>
+template <int MINB, bool FAST>
 cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a_in,
                        Counters *ctr, cudaStream_t st, int by0, int nby, int by1, int nby1)
 {
-    using TL = Tile4<TX, kTY>;
-    constexpr int SMEM = (int)((FAST ? 3 : 4) * TL::PLANE_BYTES);
-    auto kern = sweep4_kernel<TX, MINB, FAST>;
+    constexpr int SMEM = (int)((FAST ? 3 : 4) * BoxF::PLANE_BYTES);
+    auto kern = sweep4_kernel<MINB, FAST>;
     static bool attr_set[64] = { false };           // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -889,7 +886,8 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, const void *tmap_hal
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const int gy = (g.rows + kTY - 1) / kTY;
+    if (a_in.tx < 2 || a_in.ty < 2) return cudaErrorInvalidValue;      // pmc4_plan_sweep was not called
+    const int gy = (g.rows + a_in.ty - 1) / a_in.ty;
     SweepArgs a = a_in;
     a.by_off = by0;
     if (nby <= 0) { a.by_off = 0; nby = gy; }
@@ -897,35 +895,54 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, const void *tmap_hal
     if (nby <= 0) return cudaSuccess;
     a.by_n1 = nby; a.by_off2 = by1;
     if (nby1 < 0 || by1 + nby1 > gy) nby1 = 0;
-    dim3 grid((g.cps + TX - 1) / TX, nby + nby1);
+    dim3 grid((g.cps + a.tx - 1) / a.tx, nby + nby1);
     kern<<<grid, kNT, SMEM, st>>>(*(const CUtensorMap *)tmap_in, *(const CUtensorMap *)tmap_half, dout, g, a, ctr);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-int pmc4_tile_count(const Geom4 &g) { return ((g.cps + kTXN - 1) / kTXN) * ((g.rows + kTY - 1) / kTY); }
-int pmc4_tile_rows(const Geom4 &g) { return (g.rows + kTY - 1) / kTY; }
-int pmc4_tile_x() { return kTXN; }
-int pmc4_tile_y() { return kTY; }
+// The tiling of one sweep, from its colour order and shift (a.offx / offy / shift_* must be set).
+// A halo cell of colour k at distance d from the owned cells matters only if d later colours
+// alternate the parity along that axis (each step towards the owned cells crosses one column /
+// row), so per axis the halo is the longest parity-alternating subsequence of the colour order
+// (2, 3 or 4) and colour k is computed 1 + las(0) - las(k) cells in from the region edge.
+// The staged box is fixed (36 x 33 cells, at most 16 x 16 active cells per colour): a shallower
+// halo leaves room for more owned columns / rows.
+void pmc4_plan_sweep(SweepArgs &a, int full_halo)
+{
+    int lasx[4], lasy[4];
+    for (int k = 3; k >= 0; k--) {
+        lasx[k] = lasy[k] = 1;
+        for (int m = k + 1; m < 4; m++) {
+            if (a.offx[m] != a.offx[k] && lasx[m] + 1 > lasx[k]) lasx[k] = lasx[m] + 1;
+            if (a.offy[m] != a.offy[k] && lasy[m] + 1 > lasy[k]) lasy[k] = lasy[m] + 1;
+        }
+    }
+    if (full_halo) for (int k = 0; k < 4; k++) lasx[k] = lasy[k] = 4 - k;
+    a.hx = lasx[0]; a.hy = lasy[0];
+    a.lo_x = a.lo_y = 0;
+    for (int k = 0; k < 4; k++) {
+        a.lo_x |= (unsigned)(1 + lasx[0] - lasx[k]) << (4 * k);
+        a.lo_y |= (unsigned)(1 + lasy[0] - lasy[k]) << (4 * k);
+    }
+    const int ex = (a.shift_on && a.shift_f == 0) ? 1 : 0, ey = (a.shift_on && a.shift_f == 1) ? 1 : 0;
+    // columns: region tx + 2 hx + ex, of which all but the two edge columns can be active in colour 0: <= 32;
+    // rows: region ty + 2 hy + ey <= kSYB
+    a.tx = (34 - 2 * a.hx - ex) & ~1;
+    a.ty = (kSYB - 2 * a.hy - ey) & ~1;
+}
+
+int pmc4_tile_rows(const Geom4 &g, const SweepArgs &a) { return (g.rows + a.ty - 1) / a.ty; }
 
 // rows / chunk columns the internal array needs so that every staged box is in bounds, and the
 // extent of the crowded-cell flag grid over it
 void pmc4_alloc_shape(int cps, int rows, int *CH, int *ROWS, int *FW, int *FH)
 {
-    using TN = Tile4<kTXN, kTY>;
-    using TW = Tile4<kTXW, kTY>;
-    const int gxn = (cps + kTXN - 1) / kTXN, gxw = (cps + kTXW - 1) / kTXW, gy = (rows + kTY - 1) / kTY;
-    // last staged column: kMX + (gx-1)*TX - H - 1 (rounded down to even) + 2*HB - 1
-    const int cn = kMX + (gxn - 1) * kTXN - TN::H + 2 * TN::HB + 2;
-    const int cw = kMX + (gxw - 1) * kTXW - TW::H + 2 * TW::HB + 2;
-    int cc = cn > cw ? cn : cw;
-    const int cols_img = cps + 2 * kMX;
-    cc = cc > cols_img ? cc : cols_img;
-    *CH = (cc + 1) / 2;
-    const int r = kMY + (gy - 1) * kTY - TN::H + TN::SYB + 1;
-    const int r_img = rows + 2 * kMY;
-    *ROWS = r > r_img ? r : r_img;
+    // a box starts at most 5 cells before its first owned column / row, the last tile starts before cps / rows
+    const int cols = kMX + cps + BoxF::PITCH + 2, rws = kMY + rows + kSYB + 2;
+    *CH = (cols + 1) / 2;
+    *ROWS = rws;
     *FW = ((2 * *CH) >> kFB) + 1;
     *FH = (*ROWS >> kFB) + 1;
 }
@@ -941,7 +958,7 @@ int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g, int
         if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)(e != cudaSuccess ? e : cudaErrorNotSupported);
         encode = (EncodeTiledFn)fn;
     }
-    const int hb = Tile4<kTXN, kTY>::HB, syb = half ? Tile4<kTXN, kTYS>::SYB : Tile4<kTXN, kTY>::SYB;
+    const int hb = BoxF::HB, syb = half ? kSYBH : kSYB;
     const cuuint64_t dims[4] = { (cuuint64_t)4 * g.CH, 2, 4, (cuuint64_t)g.ROWS };
     const cuuint64_t strides[3] = { (cuuint64_t)g.CH * 16, (cuuint64_t)g.CH * 32, (cuuint64_t)g.CH * 128 };
     const cuuint32_t box[4] = { (cuuint32_t)(4 * hb), 2, 1, (cuuint32_t)syb };
@@ -968,15 +985,10 @@ cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, floa
 }
 
 // fast = 1: the 3-plane kernel with the crowded-cell flag lookup (tile rows whose boxes hold no
-// ghost rows); 0: the 4-plane kernel
+// ghost rows); 0: the 4-plane kernel.  a must have been planned (pmc4_plan_sweep).
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a,
                               Counters *ctr, cudaStream_t st, int fast, int by0, int nby, int by1, int nby1)
 {
-    const bool narrow = a.shift_on && a.shift_f == 0;       // the extra upstream column needs the 35th region column
-    if (fast) {
-        if (narrow) return launch_cfg<kTXN, 4, true>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
-        return launch_cfg<kTXW, 4, true>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
-    }
-    if (narrow) return launch_cfg<kTXN, 3, false>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
-    return launch_cfg<kTXW, 3, false>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
+    if (fast) return launch_cfg<4, true>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
+    return launch_cfg<3, false>(g, tmap_in, tmap_half, dout, a, ctr, st, by0, nby, by1, nby1);
 }
