@@ -92,7 +92,7 @@ struct pmc_handle {
     // slab runs: ghost rows travel on a side stream while the interior tile rows are computed
     cudaStream_t comm_stream;
     cudaEvent_t ev_boundary, ev_exchanged;
-    // crowded-cell flags of the two internal buffers (one word per 8 x 8 cells, epoch-stamped)
+    // crowded-cell flags of the two internal buffers (one word per 2 x 2 cells, epoch-stamped)
     unsigned *v4_flags[2];
     unsigned v4_epoch[2], v4_epoch_next;
     long long launches;         // kernels launched by this handle since the last pmc_reset_counters

@@ -48,7 +48,7 @@ struct SweepArgs {
     int by_off;             // fused fast path: first tile row of this launch (boundary / interior split of slab runs)
     int by_n1, by_off2;     // grid rows >= by_n1 map to tile rows by_off2 + (row - by_n1) (second band)
     int prefetch_ahead;     // fused fast path: L2-prefetch the tile of block id + this (0 = off)
-    // fused fast path: crowded-cell flags (one word per 8 x 8 block of internal cells, stamped with the
+    // fused fast path: crowded-cell flags (one word per 2 x 2 block of internal cells, stamped with the
     // epoch of the sweep that stored a cell with 7 or 8 disks there; never cleared)
     const unsigned *flag_in;    // flags of the state being read, valid where == epoch_in
     unsigned *flag_out;         // flags of the state being written, stamped with epoch_out

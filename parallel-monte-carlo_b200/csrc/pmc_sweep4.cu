@@ -15,7 +15,7 @@
 //     by the CTA that produces the original cell (single GPU) or by the NCCL ring (slab rows),
 //     so a tile never wraps.
 //   * cells hold <= 6 disks in all but ~1e-5 of the cases at phi = 0.70, w = 2 sigma.  Every
-//     store records, per block of 8 x 8 internal cells, whether it wrote a cell with 7 or 8
+//     store records, per block of 2 x 2 internal cells, whether it wrote a cell with 7 or 8
 //     disks (an epoch-stamped flag word, so nothing is ever cleared).  A tile whose staged box
 //     touches no flagged block takes the FAST path: plane P3 is not even staged (3 TMA boxes,
 //     56 KB of shared memory, 64 registers: FOUR CTAs per SM instead of three) and the NS = 6
@@ -40,7 +40,7 @@ namespace {
 constexpr float kSent = PMC_SENTINEL;
 constexpr float kSentTest = 1.0e17f;      // x < kSentTest <=> slot in use
 constexpr int kNT = 256;                  // threads per CTA of every kernel in this file
-constexpr int kFB = 3;                    // log2 of the flag block edge (8 x 8 internal cells per flag word)
+constexpr int kFB = 1;                    // log2 of the flag block edge (2 x 2 internal cells per flag word)
 
 // The staged box: 36 columns (18 per parity) x SYB rows of cells per plane, the same for every
 // tiling.  How much of it is owned is decided per sweep (SweepArgs::tx, ty, hx, hy): the halo a sweep
@@ -216,7 +216,7 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
     return 2 * (int)(off / PS) + (step != 8u ? 1 : 0);
 }
 
-// a cell with 7 or 8 disks was produced (rare): stamp the flag word of its 8 x 8 block - and of
+// a cell with 7 or 8 disks was produced (rare): stamp the flag word of its 2 x 2 block - and of
 // the blocks of its periodic images - so that the next sweep stages P3 for the tiles that see it;
 // on the fast path (P3 not in shared memory) also write its P3 chunk, images included
 __device__ __noinline__ void crowded_cell_out(float4 *dout, unsigned *flag_out, unsigned epoch, int cps, int rows,
@@ -624,13 +624,14 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     }
     int crowded = 0;
     if (NPL == 3) {
-        // at most 6 x 5 flag blocks under the 36 x 33 box: one lane each, while the TMA is in flight
-        if (tid < 30 && !(a.dbg_skip & 32)) {
-            const int bx = (Xb0 >> kFB) + tid % 6, by = (t.Y0 >> kFB) + tid / 6;
-            if (bx <= ((Xb0 + TL::PITCH - 1) >> kFB) && by <= ((t.Y0 + TL::SYB - 1) >> kFB))
-                crowded = __ldg(a.flag_in + by * g.FW + bx) == a.epoch_in;
-        }
-        static_assert(NPL != 3 || (TL::PITCH + 6) / 8 + 1 <= 6 && (TL::SYB + 6) / 8 + 1 <= 5, "flag lanes");
+        // flag words under the region (every cell of it is read with the 6-slot assumption): at most
+        // 19 per row, a lane each, the warps stride over the rows; all while the TMA is in flight
+        const int bx0 = t.X0 >> kFB, nbx = ((t.X0 + t.RX - 1) >> kFB) - bx0 + 1;
+        const int by0 = t.Y0 >> kFB, nby = ((t.Y0 + t.RY - 1) >> kFB) - by0 + 1;
+        static_assert(((TL::PITCH - 1) >> kFB) + 2 <= 32, "flag lanes");
+        if ((tid & 31) < nbx && !(a.dbg_skip & 32))
+            for (int by = tid >> 5; by < nby; by += kNT / 32)
+                crowded |= __ldg(a.flag_in + (by0 + by) * g.FW + bx0 + (tid & 31)) == a.epoch_in;
         if (a.dbg_skip & 8) crowded = 1;
     }
     if (tid == 0) mbar_wait(mbar, phase);           // one poller; the others observe the completed phase once
