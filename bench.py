@@ -35,9 +35,9 @@ N_M, NMAX, SIGMA, CELL_W, SEED = 4, 8, 1.0, 2.0, 1234
 METRIC = "hard-disk trial moves/sec"
 UNIT = "moves/s"
 
-# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_v7_summary.txt):
+# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_v8_summary.txt):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 232.3e6 + 258.6e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 237.4e6 + 252.7e6}
 
 
 def algorithmic_bytes_per_sweep(n_particles, n_cells):
@@ -263,7 +263,7 @@ def main():
     if fast:
         # CUDA events bracket the sweep kernels of each pmc_sweep call (import / export excluded)
         ms_per_launch = kernel_ms / kernel_launches
-        kname = "sweep4_kernel<24|26, 4 CTAs/SM, fast> (one launch = one MC sweep: 4 colours + shiftCells)"
+        kname = "sweep4_kernel<4 CTAs/SM, fast> (one launch = one MC sweep: 4 colours + shiftCells; tile 24..30 x 24..28 cells chosen per sweep)"
     else:
         ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
         kname = "sweep_tile_kernel<4,26,32,320,2,*> (generic path)"
