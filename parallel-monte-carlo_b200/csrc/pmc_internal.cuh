@@ -58,6 +58,11 @@ struct SweepArgs {
     // computed (4 bits per colour, >= 1)
     int tx, ty, hx, hy;
     unsigned lo_x, lo_y;
+    // per colour, everything about "which cells are active" that does not depend on the tile (tiles start
+    // on even columns / rows): bits 0-3 i0, 4-7 j0 (first active column / row of the region), 8-11 / 12-15
+    // lo_x / lo_y, 16-23 / 24-31 chunk offset of the first active cell / of its left neighbour in the staged
+    // box (lane part excluded)
+    unsigned colour_word[4];
     int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
                             // 8 treat every tile as crowded, 16 never use the 4-slot instantiation
 };

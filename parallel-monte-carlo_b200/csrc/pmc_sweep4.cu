@@ -274,6 +274,7 @@ struct TileCtx {
     int nox, noy;           // owned extent after clipping at the box / slab edge
     int X0, Y0;             // internal array coordinates of region (0, 0)
     int tx, ty;             // nominal owned extent of this tiling
+    int wraps;              // the region reaches beyond the box: global cell coordinates need the periodic wrap
 };
 
 // ---- one colour: one thread per active cell (subsweep.h:242-245), own cell in registers
@@ -281,22 +282,19 @@ template <int NS, typename TL>
 __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
                                             int k, int aq, int bq, unsigned &my_trials, unsigned &my_acc)
 {
-    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
+    constexpr int PITCH = TL::PITCH, PLC = TL::PLC;
     const int cps = g.cps;
     const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
-    // cells closer than lo to the region edge are stale or irrelevant (SweepArgs::lo_x): k + 1 at most
-    const int lox = (int)((a.lo_x >> (4 * k)) & 15u), loy = (int)((a.lo_y >> (4 * k)) & 15u);
-    // first active column / row of this colour in region coordinates: warp-uniform
-    const int pi = ((int)((a.offmask >> (2 * k)) & 1u) - t.rx0) & 1;       // region-column parity of the active colour
-    const int pj = ((int)((a.offmask >> (2 * k + 1)) & 1u) - (g.row0 + t.ry0)) & 1;
-    const int i0 = lox + ((pi - lox) & 1), j0 = loy + ((pj - loy) & 1);
+    // which cells this colour works on (SweepArgs::colour_word, planned on the host: tile-independent).
+    // Cells closer than lo to the region edge are stale or irrelevant; (i0, j0) = first active cell.
+    const unsigned cw = a.colour_word[k];
+    const int i0 = (int)(cw & 15u), j0 = (int)((cw >> 4) & 15u), lox = (int)((cw >> 8) & 15u), loy = (int)((cw >> 12) & 15u);
     const int i = i0 + 2 * aq, j = j0 + 2 * bq;
     if (!(i < t.RX - lox && j < t.RY - loy)) return;
-    // staged column is = i + xs = 2 aq + (i0 + xs): parity and half column split into a uniform and a lane part
-    const int isu = i0 + t.xs, par = isu & 1;
+    // staged chunk of a cell = a tile-independent part (in cw) + the lane part
     char *const cbase = reinterpret_cast<char *>(sm) + (2 * bq * PITCH + aq) * 16;
-    char *const cown = cbase + (j0 * PITCH + par * HB + (isu >> 1)) * 16;
-    const char *const cL = cbase + (j0 * PITCH + (1 - par) * HB + ((isu - 1) >> 1)) * 16;   // left neighbour; right = cL + 16
+    char *const cown = cbase + ((cw >> 16) & 255u) * 16;
+    const char *const cL = cbase + (cw >> 24) * 16;             // left neighbour; right = cL + 16
     const unsigned sown = smem_u32(cown);
     const float4 p0 = lds128<0>(sown), p1 = lds128<PLC * 16>(sown), p2 = lds128<2 * PLC * 16>(sown);
     float4 p3 = make_float4(kSent, kSent, 0.f, 0.f);
@@ -305,8 +303,10 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     if (cnt == 0) return;                       // subsweep.h:252-254
     const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
     int gx = t.rx0 + i, gy = g.row0 + t.ry0 + j;
-    gx += gx < 0 ? cps : 0; gx -= gx >= cps ? cps : 0;
-    gy += gy < 0 ? cps : 0; gy -= gy >= cps ? cps : 0;
+    if (t.wraps) {                              // CTA-uniform: only tiles at the edge of the box hold periodic images
+        gx += gx < 0 ? cps : 0; gx -= gx >= cps ? cps : 0;
+        gy += gy < 0 ? cps : 0; gy -= gy >= cps ? cps : 0;
+    }
     const uint32_t cell_id = (uint32_t)gy * (uint32_t)cps + (uint32_t)gx;
 
     // neighbour part of one trial: smallest d2 against the 3 neighbour cells that can hold a
@@ -604,6 +604,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     t.ox0 = HX + exl; t.oy0 = HY + eyl;
     t.nox = min(tx, cps - col0); t.noy = min(ty, g.rows - row0);
     const int Xb0 = t.X0 - t.xs;                    // first column of the staged box
+    t.wraps = t.rx0 < 0 || t.rx0 + t.RX > cps || g.row0 + t.ry0 < 0 || g.row0 + t.ry0 + t.RY > cps;
 
     // ------------------------------------------------------------ stage the tile: one TMA box per plane
     if (tid == 0) {
@@ -928,6 +929,21 @@ void pmc4_plan_sweep(SweepArgs &a, int full_halo)
         a.lo_y |= (unsigned)(1 + lasy[0] - lasy[k]) << (4 * k);
     }
     const int ex = (a.shift_on && a.shift_f == 0) ? 1 : 0, ey = (a.shift_on && a.shift_f == 1) ? 1 : 0;
+    {   // region (0, 0) sits at column col0 - hx - exl, row row0 - hy - eyl with col0, row0 (and the slab origin) even
+        const int sdir = (a.shift_d <= 0.0f) ? -1 : 1;
+        const int exl = ex && sdir < 0, eyl = ey && sdir < 0;
+        const int xs = (a.hx + exl) & 1;                                    // parity of the region's first internal column (kMX even)
+        for (int k = 0; k < 4; k++) {
+            const int lox = (int)((a.lo_x >> (4 * k)) & 15u), loy = (int)((a.lo_y >> (4 * k)) & 15u);
+            const int pi = (a.offx[k] + a.hx + exl) & 1, pj = (a.offy[k] + a.hy + eyl) & 1;
+            const int i0 = lox + ((pi - lox) & 1), j0 = loy + ((pj - loy) & 1);
+            const int isu = i0 + xs, par = isu & 1;
+            const int off_own = j0 * BoxF::PITCH + par * BoxF::HB + (isu >> 1);
+            const int off_left = j0 * BoxF::PITCH + (1 - par) * BoxF::HB + ((isu - 1) >> 1);
+            a.colour_word[k] = (unsigned)i0 | ((unsigned)j0 << 4) | ((unsigned)lox << 8) | ((unsigned)loy << 12) |
+                               ((unsigned)off_own << 16) | ((unsigned)off_left << 24);
+        }
+    }
     // columns: region tx + 2 hx + ex, of which all but the two edge columns can be active in colour 0: <= 32;
     // rows: region ty + 2 hy + ey <= kSYB
     a.tx = (34 - 2 * a.hx - ex) & ~1;
