@@ -140,6 +140,26 @@ def test_fused_sweep_bit_exact(N, sweeps, over):
     assert c["status"] == 0
 
 
+def test_every_colour_order_and_shift_direction_on_the_fast_path():
+    """The fused kernel sizes its tiles and halos from the sweep's colour order (24 orders) and shift
+    (axis, sign): 96 sweeps draw nearly all of the 96 combinations; the state must stay bit-identical
+    to the oracle after every block of 16 sweeps (cps = 66: 3 x 3 tiles with clipped edge tiles)."""
+    mc, o = pair(2 ** 14)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    seen = set()
+    for s0 in range(0, 96, 16):
+        for s in range(s0, s0 + 16):
+            order, f, d = o.schedule(s)
+            seen.add((tuple(order), f, d > 0))
+        mc.sweep(disk, n, s0, 16)
+        o.sweep(odisk, on, s0, 16)
+        assert_same_state(disk, n, odisk, on)
+    assert len(seen) >= 55 and len({k[0] for k in seen}) == 24
+    c = mc.counters()
+    assert (c["trials"], c["accepted"], c["lost"]) == (o.trials.value, o.accepted.value, o.lost)
+
+
 def test_fused_equals_per_call_protocol_and_split_calls():
     """pmc_sweep(K) == K x (4 x pmc_subsweep + pmc_shift_cells) == pmc_sweep(a) + pmc_sweep(K-a)."""
     mc, o = pair(2 ** 14)
