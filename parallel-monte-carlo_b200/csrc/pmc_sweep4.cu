@@ -3,8 +3,8 @@
 // This is the throughput path behind pmc_sweep(); pmc_sweep.cu keeps the generic kernel
 // (any n_M, w < 2 sigma, tiny boxes, the single-colour call site).
 //
-// Differences from the generic kernel, chosen to cut issued instructions AND shared-memory
-// wavefronts per trial (ncu: the LSU data pipe is the tightest resource of this path):
+// Differences from the generic kernel, chosen to cut issued instructions (ncu: the ALU pipe and
+// the issue slots are the tightest resources of this path) and shared-memory wavefronts:
 //   * INTERNAL STATE LAYOUT (handle-owned, never seen by the caller): one cell = 4 float4
 //     chunks   P0 = x0..x3   P1 = y0..y3   P2 = x4 x5 y4 y5   P3 = x6 x7 y6 y7
 //         chunk(X, Y, P) = ((Y*4 + P)*2 + (X & 1)) * CH + (X >> 1)
@@ -21,8 +21,11 @@
 //     56 KB of shared memory, 64 registers: FOUR CTAs per SM instead of three) and the NS = 6
 //     instantiation runs (3 instead of 4 chunks per neighbour cell, 24 instead of 32 pair
 //     tests per trial); if all staged cells hold <= 4 (dilute systems) NS = 4 runs and P2 is
-//     not touched either.  A flagged tile is processed by the same CTA as two half-height
-//     tiles with all four planes (they fit the same 56 KB) and NS chosen from a scan.
+//     not touched either.  A flagged tile is processed by the same CTA in two or three
+//     half-height pieces with all four planes (they fit the same 56 KB), NS chosen from a scan.
+//   * the staged box is fixed (36 x 33 cells); how much of it is owned is planned per sweep
+//     from the colour order (pmc4_plan_sweep): the halo an order needs is 2-4 cells per axis,
+//     a shallower halo leaves room for a larger tile (24..30 x 24..28 owned cells).
 //   * the cell count lives in-band: unused slots have x = sentinel; a cell with fewer than 8
 //     (6) disks carries its count in the bits of y7 (y5).  No count array on the hot path.
 //   * the grid shift of THIS sweep is applied while the tile leaves shared memory (the tile
