@@ -110,6 +110,12 @@ int  pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
 /* ---- host-side per-sweep randomness: FY_Shuffle + itoa + (f, d)  start.cu:238,241,251-252 */
 int  pmc_schedule(const pmc_handle *h, uint64_t sweep, int colour_order[4], int *f, float *d);
 void pmc_colour_to_off(int colour, int off[2]);
+/* How the fused sweep (pmc_sweep) tiles one sweep, from its colour order and shift alone (pure host
+ * function, no handle, no GPU; exposed so that the halo argument can be tested independently):
+ * out[0..3] = owned columns, owned rows, halo columns, halo rows of a tile;
+ * out[4+k], out[8+k] = colour k (in execution order) is computed only for cells at least that
+ * many columns / rows inside the staged region (>= 1). */
+int  pmc_plan_sweep(const int colour_order[4], int f, float d, int out[12]);
 
 /* ---- the loop body start.cu:237-260 as one call: n_sweeps x (4 sub-sweeps + shift),
  * sweeps numbered sweep0 .. sweep0+n_sweeps-1.  Fused fast path: one kernel per sweep. */

@@ -103,6 +103,7 @@ def lib():
     L.pmc_schedule.argtypes = [hp, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
     L.pmc_colour_to_off.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.pmc_colour_to_off.restype = None
+    L.pmc_plan_sweep.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_float, C.POINTER(C.c_int)]
     L.pmc_sweep.argtypes = [hp, vp, vp, C.c_uint64, C.c_int]
     L.pmc_get_counters.argtypes = [hp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
@@ -130,11 +131,23 @@ def lib():
 EXPORTS = ["pmc_create", "pmc_destroy", "pmc_get_geometry", "pmc_r_bytes", "pmc_disk_bytes",
            "pmc_n_bytes", "pmc_set_stream", "pmc_set_blocking", "pmc_synchronize",
            "pmc_error_string", "pmc_init_r", "pmc_assign", "pmc_subsweep", "pmc_shift_cells",
-           "pmc_schedule", "pmc_colour_to_off", "pmc_sweep", "pmc_get_counters",
+           "pmc_schedule", "pmc_colour_to_off", "pmc_plan_sweep", "pmc_sweep", "pmc_get_counters",
            "pmc_reset_counters", "pmc_get_kernel_time", "pmc_get_launch_count", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
            "pmc_disk_to_r_host", "pmc_run_host", "pmc_geometry_from_params", "pmc_rsa_host",
            "pmc_write_dump", "pmc_save_checkpoint", "pmc_load_checkpoint", "pmc_comm_unique_id", "pmc_comm_init",
            "pmc_exchange_ghosts"]
+
+
+def plan_sweep(order, f, d):
+    """Tile extent, halo and per-colour margins the fused sweep uses for this colour order and shift
+    (pmc_plan_sweep: host only)."""
+    o = (C.c_int * 4)(*order)
+    out = (C.c_int * 12)()
+    rc = lib().pmc_plan_sweep(o, int(f), float(d), out)
+    if rc:
+        raise PmcError(rc, "pmc_plan_sweep")
+    v = list(out)
+    return dict(tx=v[0], ty=v[1], hx=v[2], hy=v[3], lo_x=v[4:8], lo_y=v[8:12])
 
 
 def geometry_from_params(n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1,

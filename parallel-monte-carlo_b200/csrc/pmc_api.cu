@@ -323,6 +323,27 @@ void pmc_colour_to_off(int colour, int off[2])
     off[0] = (colour / 2) % 2;
 }
 
+int pmc_plan_sweep(const int order[4], int f, float d, int out[12])
+{
+    if (!order || !out || f < 0 || f > 1) return PMC_E_INVALID;
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int k = 0; k < 4; k++) {
+        if (order[k] < 0 || order[k] > 3) return PMC_E_INVALID;
+        int off[2];
+        pmc_colour_to_off(order[k], off);
+        a.offx[k] = off[0]; a.offy[k] = off[1];
+    }
+    a.shift_on = 1; a.shift_f = f; a.shift_d = d;
+    pmc4_plan_sweep(a, 0);
+    out[0] = a.tx; out[1] = a.ty; out[2] = a.hx; out[3] = a.hy;
+    for (int k = 0; k < 4; k++) {
+        out[4 + k] = (int)((a.lo_x >> (4 * k)) & 15u);
+        out[8 + k] = (int)((a.lo_y >> (4 * k)) & 15u);
+    }
+    return 0;
+}
+
 int pmc_schedule(const pmc_handle *h, uint64_t sweep, int order[4], int *f, float *d)
 {
     if (!h || !order || !f || !d) return PMC_E_INVALID;

@@ -120,3 +120,69 @@ def test_rsa_host_is_deterministic_and_overlap_free(built):
     with pytest.raises(pmc_b200.PmcError) as ei:
         pmc_b200.rsa_host(1024, seed=1, phi=0.62)
     assert ei.value.code == -2
+
+
+# ---------------------------------------------------------------- the fused sweep's tile planner (host logic)
+def _owned_cells_stay_exact(order, f, d, plan, shrink_x=0, shrink_y=0):
+    """Brute-force model of one tile of the fused sweep.  A cell is `bad` when its value may differ from the
+    true trajectory: everything outside the staged region is bad from the start; a cell that the true
+    dynamics updates in colour k but the tile does not compute (too close to the region edge) turns
+    bad; a computed cell turns bad when any of its 8 neighbours is bad at that moment.  Returns whether
+    every owned cell and the upstream strip of the shift are still good after the four colours.
+    shrink_* narrows the halo by that many cells (to show the planned halo is the smallest that works)."""
+    import pmc_b200
+    tx, ty = plan["tx"], plan["ty"]
+    hx, hy = plan["hx"] - shrink_x, plan["hy"] - shrink_y
+    sdir = -1 if d <= 0 else 1
+    exl, exh = int(f == 0 and sdir < 0), int(f == 0 and sdir > 0)
+    eyl, eyh = int(f == 1 and sdir < 0), int(f == 1 and sdir > 0)
+    RX, RY = tx + 2 * hx + exl + exh, ty + 2 * hy + eyl + eyh
+    # region (0, 0) is global cell (-hx - exl, -hy - eyl) of a tile whose first owned cell is (0, 0)
+    gx0, gy0 = -hx - exl, -hy - eyl
+    bad = [[False] * RX for _ in range(RY)]
+    for k, colour in enumerate(order):
+        ox, oy = pmc_b200.ParallelMC.colour_to_off(colour)
+        lox, loy = plan["lo_x"][k] - shrink_x, plan["lo_y"][k] - shrink_y
+        new = [row[:] for row in bad]
+        for j in range(RY):
+            for i in range(RX):
+                if (gx0 + i) % 2 != ox or (gy0 + j) % 2 != oy:
+                    continue
+                computed = lox <= i < RX - lox and loy <= j < RY - loy and lox >= 1 and loy >= 1
+                if not computed:
+                    new[j][i] = True
+                    continue
+                for dj in (-1, 0, 1):
+                    for di in (-1, 0, 1):
+                        jj, ii = j + dj, i + di
+                        if not (0 <= jj < RY and 0 <= ii < RX) or bad[jj][ii]:
+                            new[j][i] = True
+        bad = new
+    x0, x1 = hx + exl - exl, hx + exl + tx + exh        # owned columns plus the upstream strip
+    y0, y1 = hy + eyl - eyl, hy + eyl + ty + eyh
+    return not any(bad[j][i] for j in range(y0, y1) for i in range(x0, x1))
+
+
+def test_tile_planner_halo_is_sufficient_and_minimal_for_every_colour_order(built):
+    """pmc_plan_sweep: the halo of the fused sweep's tiles follows from the colour order (longest
+    parity-alternating subsequence per axis).  For all 24 orders x 2 shift axes x 2 signs: the planned
+    region keeps every owned cell exact in a brute-force dependency model, one halo cell less on either
+    axis does not, the box limits hold, and the average tile is larger than the fixed 24|26 x 24 one."""
+    import itertools
+    import pmc_b200
+    areas = []
+    for order in itertools.permutations(range(4)):
+        for f in (0, 1):
+            for d in (-0.3, 0.4):
+                p = pmc_b200.plan_sweep(order, f, d)
+                ex, ey = int(f == 0), int(f == 1)
+                assert 2 <= p["hx"] <= 4 and 2 <= p["hy"] <= 4
+                assert p["tx"] % 2 == 0 and p["ty"] % 2 == 0
+                assert p["tx"] + 2 * p["hx"] + ex <= 35 and p["ty"] + 2 * p["hy"] + ey <= 33      # the 36 x 33 box
+                assert (p["tx"] + 2 * p["hx"] + ex - 2 + 1) // 2 <= 16                              # 16 lanes per row
+                assert p["lo_x"][0] == 1 and p["lo_y"][0] == 1 and min(p["lo_x"] + p["lo_y"]) >= 1
+                assert _owned_cells_stay_exact(order, f, d, p)
+                assert not _owned_cells_stay_exact(order, f, d, p, shrink_x=1)
+                assert not _owned_cells_stay_exact(order, f, d, p, shrink_y=1)
+                areas.append(p["tx"] * p["ty"])
+    assert sum(areas) / len(areas) > 680

@@ -140,6 +140,22 @@ def test_fused_sweep_bit_exact(N, sweeps, over):
     assert c["status"] == 0
 
 
+@pytest.mark.parametrize("N,phi,delta,sweeps", [(2 ** 20, 0.70, 0.1, 4), (2 ** 20, 0.716, 0.1, 3), (2 ** 18, 0.30, 0.4, 4)])
+def test_fused_sweep_bit_exact_at_baseline_config_sizes(N, phi, delta, sweeps):
+    """BASELINE config 2 (N = 2^20, phi = 0.70: 542 x 542 cells, ~400 tiles, clipped edge tiles), the
+    hexatic-region density of config 3 and the dilute regime of config 5 at sizes the oracle (OpenMP
+    over same-colour cells) still finishes in seconds: positions, counts and counters bit for bit."""
+    mc, o = pair(N, phi=phi, move_delta=delta)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    mc.sweep(disk, n, 0, sweeps)
+    o.sweep(odisk, on, 0, sweeps, omp=True)
+    assert_same_state(disk, n, odisk, on)
+    c = mc.counters()
+    assert (c["trials"], c["accepted"], c["lost"]) == (o.trials.value, o.accepted.value, o.lost)
+    assert c["status"] == 0
+
+
 def test_every_colour_order_and_shift_direction_on_the_fast_path():
     """The fused kernel sizes its tiles and halos from the sweep's colour order (24 orders) and shift
     (axis, sign): 96 sweeps draw nearly all of the 96 combinations; the state must stay bit-identical
