@@ -91,7 +91,7 @@ struct pmc_handle {
     long long ktime_launches, ktime_pending_launches;
     // slab runs: ghost rows travel on a side stream while the interior tile rows are computed
     cudaStream_t comm_stream;
-    cudaEvent_t ev_boundary, ev_exchanged;
+    cudaEvent_t ev_interior[2], ev_exchanged[2];    // ping-pong by sweep parity
     // crowded-cell flags of the two internal buffers (one word per 2 x 2 cells, epoch-stamped)
     unsigned *v4_flags[2];
     unsigned v4_epoch[2], v4_epoch_next;
@@ -259,7 +259,10 @@ int pmc_destroy(pmc_handle *h)
         for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         delete h->ktime_pending;
     }
-    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_boundary); cudaEventDestroy(h->ev_exchanged); }
+    if (h->comm_stream) {
+        cudaStreamDestroy(h->comm_stream);
+        for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_interior[b]); cudaEventDestroy(h->ev_exchanged[b]); }
+    }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     free(h);
     return 0;
@@ -486,14 +489,17 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         int prio_lo = 0, prio_hi = 0;               // the exchange must not queue behind the interior tiles
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
-        CK(cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&h->ev_exchanged, cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) {
+            CK(cudaEventCreateWithFlags(&h->ev_interior[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_exchanged[b], cudaEventDisableTiming));
+        }
     }
     static const int pf_ahead = [] { const char *e = getenv("PMC_PREFETCH"); return e ? atoi(e) : 296; }();
     cudaEvent_t k0, k1;
     CK(cudaEventCreate(&k0));
     CK(cudaEventCreate(&k1));
     CK(cudaEventRecord(k0, h->stream));
+    int slab_split = 0, last_split_par = 0;         // the previous sweep ran on two streams
     for (int t = 0; t < n_sweeps; t++) {
         const uint64_t sweep = sweep0 + (uint64_t)t;
         int order[4], f;
@@ -521,23 +527,38 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         // tile rows that hold one of the kMY owned rows next to a slab face
         const int top0 = (h->g4.rows - kMY) / a.ty;
         if (h->p.n_ranks > 1 && overlap && top0 > 1 && top0 < gy) {
-            // boundary tile rows first (their boxes hold ghost rows, which carry no crowded-cell flags: the
-            // 4-plane kernel); their ghost-row exchange overlaps the interior rows (the fast kernel)
-            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, 0, 0, 1, top0, gy - top0)); h->launches += 1;
-            CK(cudaEventRecord(h->ev_boundary, h->stream));
-            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok, 1, top0 - 1)); h->launches += 1;
-            CK(cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+            // Two streams per sweep.  Side stream (high priority): the boundary tile rows (their boxes hold
+            // ghost rows, which carry no crowded-cell flags: the 4-plane kernel), then the NCCL ring with
+            // their 5 owned rows.  Main stream: the interior rows (the fast kernel), concurrently.  Sweep t's
+            // boundary kernel needs the interior of sweep t-1 (it reads its rows as halo and overwrites the
+            // buffer it read); sweep t's interior needs the boundary rows of sweep t-1 likewise.
+            const int par = t & 1;
+            if (!slab_split) {                       // first split sweep of this call: everything so far is on the main stream
+                CK(cudaEventRecord(h->ev_interior[par ^ 1], h->stream));
+                slab_split = 1;
+            } else {
+                CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[par ^ 1], 0));
+            }
+            CK(cudaStreamWaitEvent(h->comm_stream, h->ev_interior[par ^ 1], 0));
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->comm_stream, 0, 0, 1, top0, gy - top0)); h->launches += 1;
             int rc = v4_exchange_async(h, dst, h->comm_stream);
             if (rc) return rc;
-            CK(cudaEventRecord(h->ev_exchanged, h->comm_stream));
-            CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged, 0));
+            CK(cudaEventRecord(h->ev_exchanged[par], h->comm_stream));
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok, 1, top0 - 1)); h->launches += 1;
+            CK(cudaEventRecord(h->ev_interior[par], h->stream));
+            last_split_par = par;
         } else {
+            if (slab_split) {                        // back on one stream: join the side stream first
+                CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[last_split_par], 0));
+                slab_split = 0;
+            }
             CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, h->p.n_ranks == 1 ? fast_ok : 0)); h->launches += 1;
             int rc = v4_exchange_async(h, dst, h->stream);
             if (rc) return rc;
         }
         cur ^= 1;
     }
+    if (slab_split) CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[last_split_par], 0));
     CK(cudaEventRecord(k1, h->stream));
     if (!h->ktime_pending) h->ktime_pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
     h->ktime_pending->push_back(std::make_pair(k0, k1));
