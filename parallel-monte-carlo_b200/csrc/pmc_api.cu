@@ -57,6 +57,7 @@ static bool nccl_load()
 }
 
 // ------------------------------------------------------------------ handle
+constexpr int kMaxBands = 8;
 constexpr int kGhostRows = 5;   // fused sweep halo (4) + 1 upstream row of the pending shift
 
 struct pmc_handle {
@@ -92,6 +93,9 @@ struct pmc_handle {
     // slab runs: ghost rows travel on a side stream while the interior tile rows are computed
     cudaStream_t comm_stream;
     cudaEvent_t ev_interior[2], ev_exchanged[2];    // ping-pong by sweep parity
+    // single GPU: bands of tile rows on their own streams, so that the tail of sweep t overlaps the head of t+1
+    cudaStream_t band_stream[kMaxBands];
+    cudaEvent_t ev_band[2][kMaxBands], ev_band_start;
     // crowded-cell flags of the two internal buffers (one word per 2 x 2 cells, epoch-stamped)
     unsigned *v4_flags[2];
     unsigned v4_epoch[2], v4_epoch_next;
@@ -259,6 +263,12 @@ int pmc_destroy(pmc_handle *h)
         for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         delete h->ktime_pending;
     }
+    for (int b = 0; b < kMaxBands; b++)
+        if (h->band_stream[b]) {
+            cudaStreamDestroy(h->band_stream[b]);
+            cudaEventDestroy(h->ev_band[0][b]); cudaEventDestroy(h->ev_band[1][b]);
+        }
+    if (h->ev_band_start) cudaEventDestroy(h->ev_band_start);
     if (h->comm_stream) {
         cudaStreamDestroy(h->comm_stream);
         for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_interior[b]); cudaEventDestroy(h->ev_exchanged[b]); }
@@ -500,6 +510,27 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     CK(cudaEventCreate(&k1));
     CK(cudaEventRecord(k0, h->stream));
     int slab_split = 0, last_split_par = 0;         // the previous sweep ran on two streams
+    // Single GPU: the tile rows of a sweep are cut into `bands` bands, each on its own stream.  Band b of
+    // sweep t+1 reads and overwrites only what bands b-1, b, b+1 (periodic) of sweep t wrote and read, so it
+    // waits for those three alone: the last CTAs of sweep t and the first of t+1 share the GPU, there is no
+    // idle tail and no launch gap between sweeps.
+    static const int bands_env = [] { const char *e = getenv("PMC_BANDS"); return e ? atoi(e) : 6; }();
+    // at least 3 tile rows per band whatever this call's sweeps choose as tile height (<= 28 rows), at least
+    // 4 bands (with 3, every band is every other band's neighbour); fixed for the whole call
+    int bands = (h->g4.rows + 27) / 28 / 3;
+    if (bands > bands_env) bands = bands_env;
+    if (bands > kMaxBands) bands = kMaxBands;
+    if (bands < 4 || h->p.n_ranks != 1 || n_sweeps < 2) bands = 1;
+    int banded = 0, band_par = 0;                   // bands are in flight; parity of their latest events
+    if (bands > 1) {
+        for (int b = 0; b < bands; b++)
+            if (!h->band_stream[b]) {
+                CK(cudaStreamCreateWithFlags(&h->band_stream[b], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&h->ev_band[0][b], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_band[1][b], cudaEventDisableTiming));
+            }
+        if (!h->ev_band_start) CK(cudaEventCreateWithFlags(&h->ev_band_start, cudaEventDisableTiming));
+    }
     for (int t = 0; t < n_sweeps; t++) {
         const uint64_t sweep = sweep0 + (uint64_t)t;
         int order[4], f;
@@ -547,7 +578,27 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
             CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok, 1, top0 - 1)); h->launches += 1;
             CK(cudaEventRecord(h->ev_interior[par], h->stream));
             last_split_par = par;
+        } else if (bands > 1 && gy >= 3 * bands) {
+            const int par = t & 1;
+            if (!banded) {                           // everything so far (import) is on the main stream
+                CK(cudaEventRecord(h->ev_band_start, h->stream));
+                for (int b = 0; b < bands; b++) CK(cudaStreamWaitEvent(h->band_stream[b], h->ev_band_start, 0));
+            }
+            for (int b = 0; b < bands; b++) {
+                if (banded) {
+                    CK(cudaStreamWaitEvent(h->band_stream[b], h->ev_band[par ^ 1][(b + bands - 1) % bands], 0));
+                    CK(cudaStreamWaitEvent(h->band_stream[b], h->ev_band[par ^ 1][(b + 1) % bands], 0));
+                }
+                const int r0 = (int)((long long)gy * b / bands), r1 = (int)((long long)gy * (b + 1) / bands);
+                CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->band_stream[b], fast_ok, r0, r1 - r0)); h->launches += 1;
+                CK(cudaEventRecord(h->ev_band[par][b], h->band_stream[b]));
+            }
+            banded = 1; band_par = par;
         } else {
+            if (banded) {                            // back on the main stream: join every band
+                for (int b = 0; b < bands; b++) CK(cudaStreamWaitEvent(h->stream, h->ev_band[band_par][b], 0));
+                banded = 0;
+            }
             if (slab_split) {                        // back on one stream: join the side stream first
                 CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[last_split_par], 0));
                 slab_split = 0;
@@ -559,6 +610,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         cur ^= 1;
     }
     if (slab_split) CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[last_split_par], 0));
+    if (banded) for (int b = 0; b < bands; b++) CK(cudaStreamWaitEvent(h->stream, h->ev_band[band_par][b], 0));
     CK(cudaEventRecord(k1, h->stream));
     if (!h->ktime_pending) h->ktime_pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
     h->ktime_pending->push_back(std::make_pair(k0, k1));
