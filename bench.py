@@ -263,7 +263,7 @@ def main():
     if fast:
         # CUDA events bracket the sweep kernels of each pmc_sweep call (import / export excluded)
         ms_per_launch = kernel_ms / kernel_launches
-        kname = "sweep4_kernel<4 CTAs/SM, fast> (one launch = one MC sweep: 4 colours + shiftCells; tile 24..30 x 24..28 cells chosen per sweep)"
+        kname = "sweep4_kernel<4 CTAs/SM, fast> (one MC sweep = 4 colours + shiftCells; tile 24..30 x 24..28 cells chosen per sweep; single GPU: 6 band launches per sweep)"
     else:
         ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
         kname = "sweep_tile_kernel<4,26,32,320,2,*> (generic path)"
