@@ -521,9 +521,15 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     if (bands > bands_env) bands = bands_env;
     if (bands > kMaxBands) bands = kMaxBands;
     if (bands < 4 || h->p.n_ranks != 1 || n_sweeps < 2) bands = 1;
+    // slabs: the interior tile rows (all but one tile row per face) in bands likewise; only the two outer
+    // bands depend on the boundary rows and their exchange
+    int sbands = ((h->g4.rows + 27) / 28 - 4) / 3;      // 3 * sbands <= (rows - 5) / 28 - 1 <= interior tile rows of any sweep
+    if (sbands > bands_env) sbands = bands_env;
+    if (sbands > kMaxBands) sbands = kMaxBands;
+    if (sbands < 3 || h->p.n_ranks == 1 || !overlap || n_sweeps < 2) sbands = 1;
     int banded = 0, band_par = 0;                   // bands are in flight; parity of their latest events
-    if (bands > 1) {
-        for (int b = 0; b < bands; b++)
+    if (bands > 1 || sbands > 1) {
+        for (int b = 0; b < (bands > sbands ? bands : sbands); b++)
             if (!h->band_stream[b]) {
                 CK(cudaStreamCreateWithFlags(&h->band_stream[b], cudaStreamNonBlocking));
                 CK(cudaEventCreateWithFlags(&h->ev_band[0][b], cudaEventDisableTiming));
@@ -564,19 +570,42 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
             // boundary kernel needs the interior of sweep t-1 (it reads its rows as halo and overwrites the
             // buffer it read); sweep t's interior needs the boundary rows of sweep t-1 likewise.
             const int par = t & 1;
-            if (!slab_split) {                       // first split sweep of this call: everything so far is on the main stream
-                CK(cudaEventRecord(h->ev_interior[par ^ 1], h->stream));
+            const bool first_split = !slab_split;
+            const bool sb = sbands > 1;              // interior in bands: the same for every sweep of a call
+            if (first_split) {                       // first split sweep of this call: everything so far is on the main stream
+                CK(cudaEventRecord(sb ? h->ev_band_start : h->ev_interior[par ^ 1], h->stream));
                 slab_split = 1;
-            } else {
+            } else if (!sb) {
                 CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[par ^ 1], 0));
             }
-            CK(cudaStreamWaitEvent(h->comm_stream, h->ev_interior[par ^ 1], 0));
+            if (!sb) CK(cudaStreamWaitEvent(h->comm_stream, h->ev_interior[par ^ 1], 0));
+            else if (first_split) CK(cudaStreamWaitEvent(h->comm_stream, h->ev_band_start, 0));
+            else {                                   // the interior rows next to the faces
+                CK(cudaStreamWaitEvent(h->comm_stream, h->ev_band[par ^ 1][0], 0));
+                CK(cudaStreamWaitEvent(h->comm_stream, h->ev_band[par ^ 1][sbands - 1], 0));
+            }
             CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->comm_stream, 0, 0, 1, top0, gy - top0)); h->launches += 1;
             int rc = v4_exchange_async(h, dst, h->comm_stream);
             if (rc) return rc;
             CK(cudaEventRecord(h->ev_exchanged[par], h->comm_stream));
-            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok, 1, top0 - 1)); h->launches += 1;
-            CK(cudaEventRecord(h->ev_interior[par], h->stream));
+            if (!sb) {
+                CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok, 1, top0 - 1)); h->launches += 1;
+                CK(cudaEventRecord(h->ev_interior[par], h->stream));
+            } else {
+                for (int b = 0; b < sbands; b++) {
+                    cudaStream_t bs = h->band_stream[b];
+                    if (first_split) CK(cudaStreamWaitEvent(bs, h->ev_band_start, 0));
+                    else {
+                        if (b > 0) CK(cudaStreamWaitEvent(bs, h->ev_band[par ^ 1][b - 1], 0));
+                        if (b < sbands - 1) CK(cudaStreamWaitEvent(bs, h->ev_band[par ^ 1][b + 1], 0));
+                        if (b == 0 || b == sbands - 1) CK(cudaStreamWaitEvent(bs, h->ev_exchanged[par ^ 1], 0));
+                    }
+                    const int r0 = 1 + (int)((long long)(top0 - 1) * b / sbands), r1 = 1 + (int)((long long)(top0 - 1) * (b + 1) / sbands);
+                    CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, bs, fast_ok, r0, r1 - r0)); h->launches += 1;
+                    CK(cudaEventRecord(h->ev_band[par][b], bs));
+                }
+                banded = 2; band_par = par;           // 2: slab bands (joined like the single-GPU ones)
+            }
             last_split_par = par;
         } else if (bands > 1 && gy >= 3 * bands) {
             const int par = t & 1;
@@ -596,7 +625,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
             banded = 1; band_par = par;
         } else {
             if (banded) {                            // back on the main stream: join every band
-                for (int b = 0; b < bands; b++) CK(cudaStreamWaitEvent(h->stream, h->ev_band[band_par][b], 0));
+                for (int b = 0; b < (banded == 2 ? sbands : bands); b++) CK(cudaStreamWaitEvent(h->stream, h->ev_band[band_par][b], 0));
                 banded = 0;
             }
             if (slab_split) {                        // back on one stream: join the side stream first
@@ -610,7 +639,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         cur ^= 1;
     }
     if (slab_split) CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[last_split_par], 0));
-    if (banded) for (int b = 0; b < bands; b++) CK(cudaStreamWaitEvent(h->stream, h->ev_band[band_par][b], 0));
+    if (banded) for (int b = 0; b < (banded == 2 ? sbands : bands); b++) CK(cudaStreamWaitEvent(h->stream, h->ev_band[band_par][b], 0));
     CK(cudaEventRecord(k1, h->stream));
     if (!h->ktime_pending) h->ktime_pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
     h->ktime_pending->push_back(std::make_pair(k0, k1));

@@ -91,13 +91,15 @@ def test_slab_geometry_on_one_gpu(built):
 
 
 @pytest.mark.gpu
-def test_two_rank_run_is_bit_identical_to_single_gpu(built):
+@pytest.mark.parametrize("N,sweeps,port", [(2 ** 18, 7, 29611),      # one launch per part and sweep
+                                           (2 ** 22, 9, 29612)])     # 542 rows per rank: interior in 5 bands on 5 streams
+def test_two_rank_run_is_bit_identical_to_single_gpu(built, N, sweeps, port):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run by hand with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29611",
-           os.path.join(ROOT, "scripts", "slab_worker.py"), str(2 ** 18), "7"]
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "scripts", "slab_worker.py"), str(N), str(sweeps)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "bit_identical=True" in out.stdout and "protocol_identical=True" in out.stdout
