@@ -118,7 +118,10 @@ void pmc_colour_to_off(int colour, int off[2]);
 int  pmc_plan_sweep(const int colour_order[4], int f, float d, int out[12]);
 
 /* ---- the loop body start.cu:237-260 as one call: n_sweeps x (4 sub-sweeps + shift),
- * sweeps numbered sweep0 .. sweep0+n_sweeps-1.  Fused fast path: one kernel per sweep. */
+ * sweeps numbered sweep0 .. sweep0+n_sweeps-1.  Fused fast path: one kernel per sweep and band of
+ * tile rows.  The call may use a few internal CUDA streams (bands of a sweep; the slab boundary rows and
+ * their NCCL ring); they fork from and join back into the handle's stream, so for the caller the whole
+ * call is ordered on that stream exactly like a single kernel launch.  No host threads are created. */
 int  pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n_sweeps);
 
 /* ---- counters / observables (reference: unexported accept_counter kernel.cu:228,413) */
