@@ -1,8 +1,10 @@
 /* start_driver.c -- the reference's main() (start.cu:169-272) on top of the C-ABI.
  * Build:  gcc -Iinclude -I/usr/local/cuda/include examples/start_driver.c \
  *             -Lparallel-monte-carlo_b200 -lpmc_b200 -L/usr/local/cuda/lib64 -lcudart -o start_driver
- * Prints the acceptance ratio and the invariants; exit code 0 iff the per-call protocol and the
- * fused pmc_sweep agree bit for bit. */
+ * usage: start_driver [N [MCpasses [print]]]
+ * Prints the acceptance ratio and the invariants; with a third argument `print` also every position in
+ * the format of the reference's host_print_disk (start.cu:159-166; global coordinates, 2-D).
+ * Exit code 0 iff the per-call protocol and the fused pmc_sweep agree bit for bit. */
 #include "pmc.h"
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -80,6 +82,16 @@ int main(int argc, char **argv)
            trials ? (double)accepted / (double)trials : 0.0, (unsigned long long)lost, status);
     printf("particles=%lld out_of_cell=%lld min_d2=%.7f fused_equals_per_call=%d\n",
            (long long)inv[0], (long long)inv[1], min_d2, same);
+
+    if (argc > 3 && strcmp(argv[3], "print") == 0) {            /* host_print_disk start.cu:159-166, :263 */
+        pmc_geometry g;
+        pmc_get_geometry(h, &g);
+        for (long long c = 0; c < g.n_cells; c++) {
+            const float x0 = (float)(c % g.cps) * g.w - 0.5f * g.L, y0 = (float)(c / g.cps) * g.w - 0.5f * g.L;
+            for (int j = 0; j < na[c]; j++)                     /* disk[cell][dim][slot], cell-local -> global */
+                printf("Position of atom %i in cell %lld: %f\t%f\n", j, c, x0 + a[16 * c + j], y0 + a[16 * c + 8 + j]);
+        }
+    }
 
     cudaFree(d_r); cudaFree(d_disk); cudaFree(d_n); cudaFree(d_disk2); cudaFree(d_n2);   /* :266-269 */
     pmc_destroy(h);
