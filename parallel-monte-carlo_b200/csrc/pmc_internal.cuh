@@ -64,7 +64,8 @@ struct SweepArgs {
     // box (lane part excluded)
     unsigned colour_word[4];
     int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
-                            // 8 treat every tile as crowded, 16 never use the 4-slot instantiation
+                            // 8 treat every tile as crowded, 16 never use the 4-slot instantiation, 32 skip the
+                            // crowded-cell flag lookup (timing only), 64 full halo for every colour order
 };
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`)

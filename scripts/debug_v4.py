@@ -1,12 +1,12 @@
 """Development aid: isolate the phases of the v4 fused sweep with PMC_DBG_SKIP
-(1 = no sub-sweeps, 2 = no shift, 4 = no store) and compare against the oracle."""
+(1 = no sub-sweeps, 2 = no shift, 4 = no store; 8, 32, 64: see pmc_internal.cuh) and compare against the oracle."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pmc_b200
 from oracle import oracle as O
 
-skip = int(os.environ.get("PMC_DBG_SKIP", "0"))  # 8 = force the 8-slot instantiation
+skip = int(os.environ.get("PMC_DBG_SKIP", "0"))  # 8 = every tile takes the crowded-tile path, 32 = no flag lookup, 64 = full halo for every colour order
 N = int(os.environ.get("PMC_N", 2 ** 14))
 S = int(os.environ.get("PMC_S", 3))
 kw = dict(phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1, seed=1234)
