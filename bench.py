@@ -35,9 +35,48 @@ N_M, NMAX, SIGMA, CELL_W, SEED = 4, 8, 1.0, 2.0, 1234
 METRIC = "hard-disk trial moves/sec"
 UNIT = "moves/s"
 
-# ncu --set full capture of sweep4_kernel at N=2^24 phi=0.70 (profiles/r1/ncu_sweep4_v8_summary.txt):
-# dram__bytes_read.sum + dram__bytes_write.sum per launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"n16m_phi0.70": 237.4e6 + 252.7e6}
+PROFILE_ROUND = "r2"
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused sweep kernel PER SWEEP, from the committed
+    `ncu --set full` capture of this workload (profiles/<round>/traffic_<workload>.json names the command,
+    the build and the launches it summed) - or None: nothing is typed in here."""
+    path = os.path.join(ROOT, "profiles", PROFILE_ROUND, f"traffic_{workload}.json")
+    if not os.path.exists(path):
+        return None, None
+    t = json.load(open(path))
+    return float(t["dram_bytes_per_sweep"]), os.path.relpath(path, ROOT)
+
+
+def default_workload(world_env):
+    """BASELINE.json metric: N=16M phi=0.70 on 1 GPU; N=256M at 1/2/4/8 GPUs.  The scaling series is the one
+    launched through torch.distributed.run (WORLD_SIZE set, also for N=1), so all four lines share the 256M
+    workload and the driver's efficiency is 256M against 256M."""
+    return "n256m_phi0.70" if world_env else "n16m_phi0.70"
+
+
+def state_hash(torch, disk, n, g, dist):
+    """64-bit hash of the owned cells (position bits and counts), a wrapping SUM over cells of a mix of
+    (global cell id, the cell's 16 words, its count): independent of how cells are spread over ranks, so
+    the all-reduced value of a k-GPU run equals the 1-GPU value iff the states are bit-identical."""
+    M1, M2 = -7046029254386353131, -4658895280553007687         # odd 64-bit constants (as int64)
+    owned0 = g.ghost_rows * g.cps
+    ncell = g.rows * g.cps
+    w = torch.tensor([(2 * k + 1) * 0x9E3779B1 for k in range(1, 17)], dtype=torch.int64, device=disk.device)
+    total = torch.zeros((), dtype=torch.int64, device=disk.device)
+    step = 1 << 22
+    for c0 in range(0, ncell, step):
+        c1 = min(ncell, c0 + step)
+        words = disk[owned0 + c0:owned0 + c1].reshape(c1 - c0, 16).view(torch.int32).to(torch.int64)
+        h = (words * w).sum(dim=1) + n[owned0 + c0:owned0 + c1].to(torch.int64) * 0x632BE5AB
+        gid = torch.arange(c0, c1, dtype=torch.int64, device=disk.device) + g.row0 * g.cps
+        h = (h ^ (gid * M1)) * M2
+        h = h ^ (h >> 29)
+        total += (h * M1).sum()
+    if dist:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return "%016x" % (int(total.item()) & 0xFFFFFFFFFFFFFFFF)
 
 
 def algorithmic_bytes_per_sweep(n_particles, n_cells):
@@ -101,6 +140,7 @@ def cpu_baseline(workload, sweeps, omp=True):
     o = O.Oracle(N, phi=phi, sigma_d=SIGMA, cell_w=CELL_W, nmax=NMAX, n_M=N_M, move_delta=delta,
                  seed=SEED, cps_multiple=mult)
     disk, n = o.assign(o.init_r())
+    O.set_threads()                                 # every core of the affinity mask, whatever OMP_NUM_THREADS says
     t0 = time.perf_counter()
     threads = o.sweep(disk, n, 0, sweeps, omp=omp)
     dt = time.perf_counter() - t0
@@ -111,10 +151,11 @@ def run_reference(args, rank, world):
     """--impl reference: the CPU path on the box's host cores, rank 0 only."""
     if rank != 0:
         return
-    workload = args.workload or ("n16m_phi0.70" if args.gpus == 1 else "n256m_phi0.70")
+    workload = args.workload or default_workload("WORLD_SIZE" in os.environ or args.gpus > 1)
     sample_wl = workload if WORKLOADS[workload][0] <= 2 ** 24 else "n16m_phi0.70"
     sweeps = args.ref_sweeps
     from oracle import oracle as O
+    O.set_threads()             # torchrun exports OMP_NUM_THREADS=1: use the affinity mask instead
     N, phi, mult, delta = WORKLOADS[sample_wl]
     o = O.Oracle(N, phi=phi, sigma_d=SIGMA, cell_w=CELL_W, nmax=NMAX, n_M=N_M, move_delta=delta,
                  seed=SEED, cps_multiple=mult)
@@ -128,11 +169,14 @@ def run_reference(args, rank, world):
         threads = o.sweep(disk, n, 1 + k * sweeps, sweeps, omp=True)
     dt = time.perf_counter() - t0
     v = (o.trials.value - tr0) / dt
-    sample = f"{sample_wl}: {sweeps} sweeps/step from the lattice start, OpenMP over same-colour cells"
+    sample = f"{sample_wl}: {sweeps} sweeps/step from the lattice start, OpenMP over same-colour cells on {threads} threads"
+    if sample_wl != workload:
+        sample += (f"; the {workload} workload itself is NOT run on the CPU: the sample is the 16M system "
+                   "(moves/s of this path does not depend on N once the state exceeds the caches)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "higher_is_better": True, "scaling": "strong" if workload.startswith("n256m") else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "sample_workload": sample_wl, "n_M": N_M, "nmax": NMAX,
                    "cell_w": o.g.w, "move_delta": delta, "sweeps_per_step": sweeps,
@@ -186,7 +230,7 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     n_ranks = world
 
-    workload = args.workload or ("n16m_phi0.70" if n_ranks == 1 else "n256m_phi0.70")
+    workload = args.workload or default_workload("WORLD_SIZE" in os.environ or n_ranks > 1)
     N, phi, mult, delta = WORKLOADS[workload]
     if n_ranks > 1:
         mult = max(mult, 2 * n_ranks)
@@ -250,9 +294,15 @@ def main():
     # invariants after the timed region (cheap, device side)
     chk = mc.check(disk, n)
     chk_t = torch.tensor([chk["total"], chk["out_of_cell"], chk["overlaps"]], dtype=torch.float64, device="cuda")
+    min_t = torch.tensor([chk["min_d2"]], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(chk_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(min_t, op=dist.ReduceOp.MIN)
     total_particles = int(chk_t[0].item())
+    min_d2 = float(min_t.item())
+    # bit-identity across GPU counts: the same arguments give the same hash at every N
+    hash_hex = state_hash(torch, disk, n, g, dist)
+    end_sweep = sweep
 
     # roofline of the dominant kernel (the fused sweep kernel, one launch per sweep)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -262,19 +312,23 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if fast:
         # CUDA events bracket the sweep kernels of each pmc_sweep call (import / export excluded)
-        ms_per_launch = kernel_ms / kernel_launches
-        kname = "sweep4_kernel<4 CTAs/SM, fast> (one MC sweep = 4 colours + shiftCells; tile 24..30 x 24..28 cells chosen per sweep; single GPU: 6 band launches per sweep)"
+        ms_per_sweep = kernel_ms / kernel_launches
+        kname = ("sweep4_kernel<4 CTAs/SM, fast> (one MC sweep = 4 colours + shiftCells; tile 24..30 x 24..28 cells "
+                 "chosen per sweep; one sweep = several band launches of this kernel on their own streams)")
     else:
-        ms_per_launch = ms / n_sweeps_timed             # upper bound: includes 1 stand-alone shift per step
+        ms_per_sweep = ms / n_sweeps_timed              # upper bound: includes 1 stand-alone shift per step
         kname = "sweep_tile_kernel<4,26,32,320,2,*> (generic path)"
-    alg_bytes = algorithmic_bytes_per_sweep(N, g.n_cells) / n_ranks      # per launch per GPU
-    achieved = alg_bytes / (ms_per_launch * 1e-3) / 1e9
+    alg_bytes = algorithmic_bytes_per_sweep(N, g.n_cells) / n_ranks      # per sweep per GPU
+    achieved = alg_bytes / (ms_per_sweep * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(workload) if n_ranks == 1 else (None, None)
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(workload) if n_ranks == 1 else None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "launch_unit": "one MC sweep (all band launches of the fused kernel)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_move": alg_bytes * n_ranks / (tot_trials / n_sweeps_timed),
-                "ms_per_launch": ms_per_launch,
+                "ms_per_sweep": ms_per_sweep,
+                "limiter": "instruction issue, not DRAM (ncu: profiles/%s); the HBM figure is the contract's roofline" % PROFILE_ROUND,
                 "issue_ceiling_lane_instr_per_s": 148 * 128 * 1.965e9}
 
     # end to end through the C-ABI with host buffers (single GPU only: slabs keep state on device)
@@ -357,7 +411,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_ranks, "steps": args.steps,
             "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if n_ranks > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+            "scaling": "strong" if workload.startswith("n256m") else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload, "n_particles": N, "phi": phi, "cells_per_side": g.cps,
                        "cell_w": g.w, "nmax": NMAX, "n_M": N_M, "move_delta": delta,
@@ -367,7 +421,10 @@ def main():
                        "parallelism": "1 GPU" if n_ranks == 1 else f"{n_ranks} slabs of {g.rows} cell rows, NCCL ghost-row ring"},
             "acceptance": tot_acc / tot_trials, "trials": tot_trials, "lost": tot_lost, "status": int(status),
             "invariants": {"particles": total_particles, "out_of_cell": int(chk_t[1].item()),
-                           "overlaps_below_sigma": int(chk_t[2].item()), "min_d2": chk["min_d2"]},
+                           "overlaps_below_sigma": int(chk_t[2].item()), "min_d2": min_d2,
+                           "state_hash": hash_hex, "state_hash_after_sweeps": int(end_sweep),
+                           "what": "hash = wrapping 64-bit sum over owned cells of mix(global cell id, position bits, count), "
+                                   "all-reduced: equal at every GPU count iff the states are bit-identical"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(gpu_launches),
         }

@@ -13,6 +13,11 @@
  *       0            success
  *       > 0          a cudaError_t value
  *       < 0          PMC_E_* below
+ *     A BLOCKING call during which a cell overflowed nmax or particles fell outside the box returns
+ *     PMC_E_OVERFLOW / PMC_E_LOST (once per event; the arrays are complete except for the dropped
+ *     particles, the `lost` counter and the status bits of pmc_get_counters keep the totals).  Non-blocking
+ *     callers poll pmc_get_counters.  pmc_create refuses geometries whose mean cell occupancy leaves less
+ *     than two free slots (PMC_E_UNSUPPORTED).
  *   - one host thread, calls are blocking unless pmc_set_blocking(h, 0)
  *   - array semantics [cell][dim][slot] + short counts (start.cu:135-137,144):
  *       disk : float[n_cells][2][nmax], n : int16[n_cells], cell = cx + cy*cps
@@ -22,6 +27,16 @@
  *   - coordinates stored in `disk` are CELL-LOCAL, in (0, w] (float32 global coordinates
  *     lose 2.4e-4 sigma at N=2^24); pmc_disk_to_r_host converts back to global coordinates.
  *     Unused slots hold x = PMC_SENTINEL, y = 0 (the reference leaves garbage).
+ *   - COORDINATE GRID: every stored coordinate, the cell width w, every shift distance d and
+ *     every trial displacement is an integer multiple of q = 2^e (pmc_geometry.grid_q; 2^-21
+ *     for 2 <= w < 4), with e chosen so that every multiple of q below 2^(e+24) > 2w is exact
+ *     in binary32.  Hence x - d, D +- w (shiftCells.h:62,97) and px -+ w (apply_PBC
+ *     subsweep.h:139-151) are exact: the grid shift is an exact translation, a pair's squared
+ *     distance fmaf(dx, dx, dy*dy) is the same number in every cell frame and after every
+ *     later shift, and "no pair with d2 < sigma_d^2" is an EXACT invariant of a trajectory
+ *     (pmc_check: overlaps == 0, min_d2 >= sigma_d^2, bit for bit).  pmc_assign snaps the
+ *     incoming coordinates to the grid (<= q/2 = 2.4e-7), pmc_schedule draws d on the grid,
+ *     pmc_shift_cells rounds a caller-chosen d to it, move_delta is rounded down to it.
  *   - compile-time #defines (start.cu:14-24) become the runtime pmc_params.
  *   - cuRAND XORWOW seeded identically on every launch (subsweep.h:259) becomes a
  *     counter-based Philox4x32-10 stream keyed on (seed, sweep, cell, trial).
@@ -79,6 +94,7 @@ typedef struct pmc_geometry {
     int     rows;           /* number of cell rows owned by this rank */
     int     ghost_rows;     /* ghost rows stored below and above the owned rows (0 if 1 rank) */
     int64_t local_cells;    /* (rows + 2*ghost_rows) * cps: cells in this rank's disk / n arrays */
+    float   grid_q;         /* coordinate grid quantum (see "coordinate grid" above); move_delta and w are multiples */
 } pmc_geometry;
 
 typedef struct pmc_handle pmc_handle;
@@ -95,6 +111,11 @@ size_t pmc_n_bytes(const pmc_handle *h);      /* local_cells * sizeof(int16_t)  
 int  pmc_set_stream(pmc_handle *h, void *cuda_stream);   /* default: a handle-owned stream */
 int  pmc_set_blocking(pmc_handle *h, int blocking);      /* default 1 (start.cu syncs after every launch) */
 int  pmc_synchronize(pmc_handle *h);
+/* Knobs that choose WHICH kernel / schedule computes the result, never the result itself (bit-identical for
+ * every setting; tests use them to drive the rare paths): "bands" 1..8, "prefetch" >= 0, "overlap" 0/1,
+ * "generic" 0/1, "force_crowded" 0/1, "no_ns4" 0/1, "full_halo" 0/1.  Unknown name: PMC_E_INVALID.
+ * The library reads no environment variable that can change a result. */
+int  pmc_set_tuning(pmc_handle *h, const char *name, int value);
 const char *pmc_error_string(int code);
 
 /* ---- the four kernel call sites */
@@ -148,6 +169,8 @@ int  pmc_pressure_from_hist(const pmc_handle *h, const uint64_t *hist_host, floa
  * cell-then-slot order; returns the particle count in *n_found. */
 int  pmc_disk_to_r_host(pmc_handle *h, const float *d_disk, const int16_t *d_n,
                         float *r_host, int64_t *n_found);
+/* the same conversion with the result left on the device (d_r: SoA [2][N], device pointer) */
+int  pmc_disk_to_r(pmc_handle *h, const float *d_disk, const int16_t *d_n, float *d_r, int64_t *n_found);
 
 /* ---- initial configurations, trajectory, checkpoint
  * Random sequential addition of n_particles disks (host code, no device needed; r_host is SoA

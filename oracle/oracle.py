@@ -20,8 +20,14 @@ class Geom(C.Structure):
         ("nmax", C.c_int), ("n_M", C.c_int), ("w", C.c_float), ("L", C.c_float),
         ("half_L", C.c_float), ("sigma", C.c_float), ("sigma2", C.c_float),
         ("delta", C.c_float), ("dscale", C.c_float), ("L_box", C.c_double),
-        ("seed", C.c_uint64),
+        ("seed", C.c_uint64), ("K", C.c_int), ("M", C.c_int),
     ]
+
+
+class TrialRecord(C.Structure):
+    _fields_ = [("sweep", C.c_uint64), ("cx", C.c_int32), ("cy", C.c_int32), ("slot", C.c_int32),
+                ("cnt", C.c_int32), ("verdict", C.c_int32), ("trial", C.c_int32),
+                ("px", C.c_float), ("py", C.c_float), ("own_x", C.c_float * 8), ("own_y", C.c_float * 8)]
 
 
 def build(force=False):
@@ -49,6 +55,10 @@ def lib():
         _lib.oracle_assign.restype = C.c_int64
         _lib.oracle_cell_of.argtypes = [gp, C.c_float]
         _lib.oracle_subsweep.argtypes = [gp, fp, sp, C.POINTER(C.c_int), C.c_uint64, u64p, u64p]
+        _lib.oracle_trial.argtypes = [gp, fp, sp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp]
+        _lib.oracle_set_trace.argtypes = [C.c_void_p, C.c_int64]
+        _lib.oracle_set_trace.restype = None
+        _lib.oracle_trace_count.restype = C.c_int64
         _lib.oracle_shift_cells.argtypes = [gp, fp, sp, C.c_int, C.c_float]
         _lib.oracle_shift_cells.restype = C.c_int64
         _lib.oracle_schedule.argtypes = [gp, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), fp]
@@ -57,6 +67,7 @@ def lib():
         _lib.oracle_sweep.restype = C.c_int64
         _lib.oracle_sweep_omp.argtypes = [gp, fp, sp, C.c_uint64, C.c_int, u64p, u64p,
                                           C.POINTER(C.c_int64)]
+        _lib.oracle_set_threads.argtypes = [C.c_int]
         _lib.oracle_disk_to_r.argtypes = [gp, fp, sp, fp]
         _lib.oracle_disk_to_r.restype = C.c_int64
         _lib.oracle_check.argtypes = [gp, fp, sp, C.POINTER(C.c_int64), fp]
@@ -70,6 +81,14 @@ def _f(a):
 
 def _s(a):
     return a.ctypes.data_as(C.POINTER(C.c_int16))
+
+
+def set_threads(n=0):
+    """OpenMP threads of the timed CPU baseline; n = 0: every core this process may run on
+    (sched_getaffinity), whatever OMP_NUM_THREADS says (torchrun exports 1)."""
+    if n <= 0:
+        n = len(os.sched_getaffinity(0))
+    return int(lib().oracle_set_threads(n))
 
 
 def philox(ctr, key):
@@ -128,6 +147,22 @@ class Oracle:
         o = (C.c_int * 2)(*off)
         lib().oracle_subsweep(C.byref(self.g), _f(disk), _s(n), o, sweep,
                               C.byref(self.trials), C.byref(self.accepted))
+
+    def trial(self, disk, n, cx, cy, slot, px, py):
+        """(verdict, min_d2) of one trial: 0 accepted, 1 out of bound, 2 overlap (oracle_trial)."""
+        md2 = C.c_float(np.float32(3.4e38))
+        v = lib().oracle_trial(C.byref(self.g), _f(disk), _s(n), cx, cy, slot, C.c_float(px), C.c_float(py),
+                               C.byref(md2))
+        return v, np.float32(md2.value)
+
+    def trace_on(self, cap):
+        self._trace = (TrialRecord * cap)()
+        lib().oracle_set_trace(C.cast(self._trace, C.c_void_p), cap)
+
+    def trace_off(self):
+        k = min(int(lib().oracle_trace_count()), len(self._trace))
+        lib().oracle_set_trace(None, 0)
+        return [self._trace[i] for i in range(k)]
 
     def shift_cells(self, disk, n, f, d):
         self.lost += lib().oracle_shift_cells(C.byref(self.g), _f(disk), _s(n), f, C.c_float(d))

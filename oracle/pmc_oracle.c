@@ -40,20 +40,35 @@ int oracle_make_geom(int64_t n_particles, float phi, float sigma_d, float cell_w
     int64_t cps = (int64_t)floor(L_d / ((double)cps_multiple * (double)cell_w)) * cps_multiple;
     if (cps < 4 || cps > 46340) return 2;
     double w_d = L_d / (double)cps;
+    /* COORDINATE GRID.  Every stored coordinate, the cell width w, every shift distance d and
+     * every trial displacement is an integer multiple of q = 2^e, with e chosen so that all
+     * multiples of q below 2^(e+24) > 2w are exactly representable in binary32.  Then x - d,
+     * D +- w (shiftCells.h:62,97), px -+ w (apply_PBC subsweep.h:139-151) and every coordinate
+     * difference are EXACT, so the grid shift is an exact translation, a pair's squared distance
+     * fmaf(dx, dx, dy*dy) is the same number in every cell frame and at every later sweep, and
+     * "no pair with d2 < sigma2" is an exact, bit-level invariant of the trajectory. */
+    int ex;
+    (void)frexp(2.0 * w_d, &ex);                 /* 2w = m * 2^ex, m in [0.5, 1) */
+    double q = ldexp(1.0, ex - 24);
+    double K = nearbyint(w_d / q);               /* cell width in grid units, < 2^23 */
+    double M = floor((double)move_delta / q);    /* proposal half-width in grid units */
+    if (M < 1.0 || M >= 4194304.0 || (double)move_delta > w_d) return 1;
     memset(g, 0, sizeof(*g));
     g->n_particles = n_particles;
     g->cps = (int)cps;
     g->n_cells = cps * cps;
     g->nmax = nmax;
     g->n_M = n_M;
-    g->w = (float)w_d;
+    g->w = (float)(K * q);
+    g->K = (int)K;
+    g->M = (int)M;
     g->L_box = (double)cps * (double)g->w;
     g->L = (float)g->L_box;
     g->half_L = g->L / 2.0f;
     g->sigma = sigma_d;
     g->sigma2 = sigma_d * sigma_d;
-    g->delta = move_delta;
-    g->dscale = move_delta * 1.1920928955078125e-07f; /* 2^-23, exact scaling */
+    g->delta = (float)(M * q);                        /* move_delta rounded down to the grid */
+    g->dscale = (float)q;                             /* one grid step */
     g->seed = seed;
     return 0;
 }
@@ -127,13 +142,14 @@ int oracle_cell_of(const oracle_geom *g, float x)
     return c;
 }
 
+/* global -> cell-local, snapped to the coordinate grid: k * q with k in [1, K] */
 static inline float to_local(const oracle_geom *g, float x, int c)
 {
     double origin = (double)c * (double)g->w - g->L_box * 0.5;
-    float xl = (float)((double)x - origin);
-    if (xl > g->w) xl = g->w;
-    if (!(xl > 0.0f)) xl = FLT_MIN;
-    return xl;
+    double k = nearbyint(((double)x - origin) / (double)g->dscale);   /* exact scaling, ties to even */
+    if (k > (double)g->K) k = (double)g->K;
+    if (k < 1.0) k = 1.0;
+    return (float)(k * (double)g->dscale);
 }
 
 static inline float to_global(const oracle_geom *g, float xl, int c)
@@ -196,15 +212,52 @@ int64_t oracle_disk_to_r(const oracle_geom *g, const float *disk, const int16_t 
 
 static inline int wrap(int c, int cps) { return c < 0 ? c + cps : (c >= cps ? c - cps : c); }
 
-/* hard-disk form of calculate_pair_energy (subsweep.h:90-103): energy is +inf iff
- * r < sigma_d.  (pxs, pys) is the trial point already expressed in the frame of the
- * cell that holds (qx, qy). */
-static inline int overlaps(float pxs, float pys, float qx, float qy, float sigma2)
+static oracle_trial_record *g_trace = NULL;
+static int64_t g_trace_cap = 0, g_trace_n = 0;
+void oracle_set_trace(oracle_trial_record *buf, int64_t cap) { g_trace = buf; g_trace_cap = cap; g_trace_n = 0; }
+int64_t oracle_trace_count(void) { return g_trace_n; }
+
+/* accept_move subsweep.h:194-217 for hard disks: the proposal is rejected when it leaves the
+ * cell (out_of_bound :73-88) or when the new energy is +inf, i.e. some other disk of the own
+ * cell (calculate_energy_in_cell :105-117, j != i) or of the 8 neighbour cells
+ * (get_neighbors :119-137 with helper {0,-1,1}, calculate_energy_in_neighbors :153-172)
+ * lies closer than sigma_d.  apply_PBC (:139-151) is implicit in cell-local coordinates: the
+ * trial point is expressed in the neighbour's frame by subtracting helper * w (exact on the
+ * coordinate grid). */
+int oracle_trial(const oracle_geom *g, const float *disk, const int16_t *n,
+                 int cx, int cy, int slot, float px, float py, float *min_d2)
 {
-    float dx = pxs - qx;
-    float dy = pys - qy;
-    float d2 = fmaf(dx, dx, dy * dy);
-    return d2 < sigma2;
+    static const int helper[3] = { 0, -1, 1 };            /* subsweep.h:120 */
+    const int nm = g->nmax, cps = g->cps;
+    const float w = g->w;
+    const int64_t cell = cx + (int64_t)cy * cps;          /* subsweep.h:14-16 */
+    const float *X = disk + cell * 2 * nm, *Y = X + nm;
+    const int cnt = n[cell];
+    /* out_of_bound subsweep.h:73-88 (half-open like assign / shiftCells) */
+    if (!(px > 0.0f && px <= w && py > 0.0f && py <= w)) return 1;
+    float md2 = FLT_MAX;
+    for (int j = 0; j < cnt; j++) {                       /* subsweep.h:105-117 */
+        if (j == slot) continue;
+        float dx = px - X[j], dy = py - Y[j];
+        float d2 = fmaf(dx, dx, dy * dy);
+        if (d2 < md2) md2 = d2;
+    }
+    for (int i = 0; i < 3; i++)                           /* subsweep.h:119-137 */
+        for (int j = 0; j < 3; j++) {
+            if (i == 0 && j == 0) continue;
+            int nx = wrap(cx + helper[i], cps), ny = wrap(cy + helper[j], cps);
+            int64_t nb = nx + (int64_t)ny * cps;
+            const float *QX = disk + nb * 2 * nm, *QY = QX + nm;
+            float pxs = px - (float)helper[i] * w;
+            float pys = py - (float)helper[j] * w;
+            for (int k = 0; k < n[nb]; k++) {             /* subsweep.h:153-172 */
+                float dx = pxs - QX[k], dy = pys - QY[k];
+                float d2 = fmaf(dx, dx, dy * dy);
+                if (d2 < md2) md2 = d2;
+            }
+        }
+    if (min_d2) *min_d2 = md2;
+    return md2 < g->sigma2 ? 2 : 0;
 }
 
 /* one active cell: subsweep.h:250-298 */
@@ -212,9 +265,7 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
                           int cx, int cy, uint64_t sweep,
                           uint64_t *trials, uint64_t *accepted)
 {
-    static const int helper[3] = { 0, -1, 1 };            /* subsweep.h:120 */
     const int nm = g->nmax, cps = g->cps;
-    const float w = g->w;
     int64_t cell = cx + (int64_t)cy * cps;                /* subsweep.h:14-16 */
     int cnt = n[cell];
     if (cnt == 0) return;                                 /* subsweep.h:252-254 */
@@ -237,38 +288,30 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
         t = X[s]; X[s] = X[j]; X[j] = t;
         t = Y[s]; Y[s] = Y[j]; Y[j] = t;
     }
+    const uint32_t nM2 = 2u * (uint32_t)g->M + 1u;
     for (int s = 0; s < g->n_M; s++) {                    /* subsweep.h:279 */
         uint32_t ra = words[2 * s], rb = words[2 * s + 1];
         int slot = s % cnt;                               /* i = (i+1) mod atom_counts, subsweep.h:291-296 */
-        /* make_move subsweep.h:60-71; proposal = uniform in the square:
-         * (odd integer, |.| < 2^23) times delta*2^-23: an exactly symmetric set of 2^23 values per
-         * axis, 2k + 1 with k = (top 23 random bits) - 2^22; one fused rounding per axis.  (The
-         * low 8 bits of the words feed the shuffle above; bit 8 is unused.) */
-        float fmx = fmaf((float)(int)(ra >> 9) - 4194304.0f, 2.0f, 1.0f);
-        float fmy = fmaf((float)(int)(rb >> 9) - 4194304.0f, 2.0f, 1.0f);
-        float px = fmaf(fmx, g->dscale, X[slot]);
-        float py = fmaf(fmy, g->dscale, Y[slot]);
+        /* make_move subsweep.h:60-71; proposal = uniform in the square on
+         * the coordinate grid: m * q per axis with m = floor((2 r24 + 1) * (2M+1) / 2^25) - M from
+         * the top 24 bits r24 of the word.  P(m) == P(-m) exactly: r24 -> 2^24 - 1 - r24 maps the
+         * odd number 2 r24 + 1 to 2^25 - (2 r24 + 1), and odd * odd / 2^25 is never an integer, so
+         * the floor maps m to -m.  A symmetric proposal is all detailed balance needs.  (The low 8
+         * bits of the words feed the shuffle above.)  x + m*q is exact. */
+        int mx = (int)((((uint64_t)(ra >> 8) * 2u + 1u) * nM2) >> 25) - g->M;
+        int my = (int)((((uint64_t)(rb >> 8) * 2u + 1u) * nM2) >> 25) - g->M;
+        float px = fmaf((float)mx, g->dscale, X[slot]);
+        float py = fmaf((float)my, g->dscale, Y[slot]);
         (*trials)++;
-        /* out_of_bound subsweep.h:73-88 (half-open like assign/shiftCells) */
-        if (!(px > 0.0f && px <= w && py > 0.0f && py <= w)) continue;
-        int hit = 0;
-        /* calculate_energy_in_cell subsweep.h:105-117 */
-        for (int j = 0; j < cnt; j++)
-            if (j != slot && overlaps(px, py, X[j], Y[j], g->sigma2)) hit = 1;
-        /* get_neighbors + calculate_energy_in_neighbors subsweep.h:119-172;
-         * apply_PBC (subsweep.h:139-151) is implicit in cell-local coordinates */
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) {
-                if (i == 0 && j == 0) continue;
-                int nx = wrap(cx + helper[i], cps), ny = wrap(cy + helper[j], cps);
-                int64_t nb = nx + (int64_t)ny * cps;
-                const float *QX = disk + nb * 2 * nm, *QY = QX + nm;
-                float pxs = px - (float)helper[i] * w;
-                float pys = py - (float)helper[j] * w;
-                for (int k = 0; k < n[nb]; k++)
-                    if (overlaps(pxs, pys, QX[k], QY[k], g->sigma2)) hit = 1;
-            }
-        if (!hit) {                                       /* accept_move subsweep.h:194-217 */
+        int verdict = oracle_trial(g, disk, n, cx, cy, slot, px, py, NULL);
+        if (g_trace && g_trace_n < g_trace_cap) {
+            oracle_trial_record *t = g_trace + g_trace_n;
+            t->sweep = sweep; t->cx = cx; t->cy = cy; t->slot = slot; t->cnt = cnt;
+            t->verdict = verdict; t->trial = s; t->px = px; t->py = py;
+            for (int k = 0; k < 8; k++) { t->own_x[k] = k < cnt ? X[k] : PMC_SENTINEL; t->own_y[k] = k < cnt ? Y[k] : 0.0f; }
+        }
+        if (g_trace) g_trace_n++;
+        if (verdict == 0) {                               /* accept_move subsweep.h:194-217 */
             X[slot] = px; Y[slot] = py;                   /* cpy_proposed_to_D_sh :219-223 */
             (*accepted)++;
         }
@@ -332,6 +375,7 @@ static int shift_cell(const oracle_geom *g, const float *src, const int16_t *nsr
 
 int64_t oracle_shift_cells(const oracle_geom *g, float *disk, int16_t *n, int f, float d)
 {
+    d = (float)(nearbyint((double)d / (double)g->dscale) * (double)g->dscale);   /* onto the coordinate grid */
     size_t db = (size_t)g->n_cells * 2 * g->nmax * sizeof(float);
     size_t nb = (size_t)g->n_cells * sizeof(int16_t);
     float *src = (float *)malloc(db);
@@ -367,8 +411,9 @@ void oracle_schedule(const oracle_geom *g, uint64_t sweep, int order[4], int *f,
         int t = order[i]; order[i] = order[j]; order[j] = t;
     }
     *f = (int)(a[3] >> 31);
-    float u = (float)((b[0] >> 8) + 1u) * 5.9604644775390625e-08f;  /* (0, 1] */
-    *d = (u - 0.5f) * g->w;                                          /* (-w/2, w/2] */
+    /* d uniform on the grid points of (-w/2, w/2] (kernel.cu:684 range): dk * q */
+    int64_t dk = (int64_t)(((uint64_t)b[0] * (uint64_t)g->K) >> 32) + 1 - (g->K + 1) / 2;
+    *d = (float)dk * g->dscale;
 }
 
 int64_t oracle_sweep(const oracle_geom *g, float *disk, int16_t *n,
@@ -388,6 +433,19 @@ int64_t oracle_sweep(const oracle_geom *g, float *disk, int16_t *n,
         lost += oracle_shift_cells(g, disk, n, f, d);      /* start.cu:255 */
     }
     return lost;
+}
+
+/* thread count of oracle_sweep_omp: torchrun exports OMP_NUM_THREADS=1 to its workers, the CPU arm of
+ * bench.py sets the count from sched_getaffinity explicitly instead.  Returns the count now in force. */
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 int oracle_sweep_omp(const oracle_geom *g, float *disk, int16_t *n,

@@ -16,9 +16,16 @@
  *   - assign / shiftCells against outputs of the reference's own kernels
  *     (kernel.cu, V2 shiftCells.h) compiled from /root/reference into oracle/_ref and
  *     executed on a B200 (tests/golden/ref_*.json, generator oracle/ref_harness.cu);
- *   - the sub-sweep itself uses a counter-based Philox stream instead of the
- *     reference's cuRAND XORWOW stream, so its trajectories are "parity unpinned"
- *     against the reference and pinned only structurally + statistically.
+ *   - the sub-sweep's per-trial decision (oracle_trial: out_of_bound, in-cell and neighbour
+ *     energies, PBC) against the reference's OWN device functions out_of_bound,
+ *     get_neighbors, apply_PBC, calculate_energy_in_cell, calculate_energy_in_neighbors
+ *     (subsweep.h:73-172), compiled unmodified from /root/reference and run on a B200 on
+ *     (state, proposal) probes: tests/golden/ref_trials_*.json, generator
+ *     oracle/ref_harness_v1.cu + tests/golden/make_trial_probes.py;
+ *   - the random stream is a counter-based Philox4x32-10 instead of the reference's cuRAND
+ *     XORWOW stream (which the reference re-seeds identically on every launch,
+ *     subsweep.h:259), so WHICH proposals are drawn is ours; what is done with a proposal
+ *     is pinned as above.
  *
  * Layout contract shared with the CUDA library (include/pmc.h):
  *   disk : float[n_cells][2][nmax]   cell-major, then dim, then slot
@@ -48,10 +55,12 @@ typedef struct {
     float   half_L;     /* L / 2 (exact halving) */
     float   sigma;      /* disk diameter */
     float   sigma2;     /* fl(sigma*sigma) */
-    float   delta;      /* proposal half-width */
-    float   dscale;     /* delta * 2^-24 */
+    float   delta;      /* proposal half-width, rounded down to the grid: M * q */
+    float   dscale;     /* q: the coordinate grid quantum (a power of two, see oracle_make_geom) */
     double  L_box;      /* cps * (double)w */
     uint64_t seed;
+    int     K;          /* w / q: cell width in grid units (< 2^23) */
+    int     M;          /* delta / q: proposals are m * q, m uniform-symmetric in [-M, M] */
 } oracle_geom;
 
 /* a1: #define block start.cu:14-27 -> runtime geometry.  cps_multiple: 2 normally. */
@@ -75,7 +84,28 @@ void oracle_subsweep(const oracle_geom *g, float *disk, const int16_t *n,
                      const int off[2], uint64_t sweep,
                      uint64_t *trials, uint64_t *accepted);
 
-/* a17: shiftCells (V2 shiftCells.h:23-112).  Returns number of particles lost. */
+/* One trial of subsweep.h:279-297 for the particle in `slot` of cell (cx, cy) proposed at
+ * (px, py) (cell-local): 0 = accepted, 1 = out of bound (subsweep.h:73-88), 2 = overlap
+ * (the hard-disk form of new_energy = +inf, subsweep.h:105-117,153-172).  *min_d2 = smallest
+ * squared distance to any other disk of the 3 x 3 block (FLT_MAX if none; only set when in
+ * bounds).  This is the function oracle_subsweep itself calls for every trial. */
+int oracle_trial(const oracle_geom *g, const float *disk, const int16_t *n,
+                 int cx, int cy, int slot, float px, float py, float *min_d2);
+
+/* Optional trace of every trial oracle_subsweep / oracle_sweep (serial versions) execute:
+ * the own cell as the trial sees it (after the shuffle and the earlier trials), the proposal
+ * and the verdict.  Used to generate the probes fed to the reference's device functions. */
+typedef struct {
+    uint64_t sweep;
+    int32_t  cx, cy, slot, cnt, verdict, trial;
+    float    px, py;
+    float    own_x[8], own_y[8];
+} oracle_trial_record;
+void oracle_set_trace(oracle_trial_record *buf, int64_t cap);   /* NULL: off */
+int64_t oracle_trace_count(void);
+
+/* a17: shiftCells (V2 shiftCells.h:23-112).  Returns number of particles lost.
+ * d is rounded to the coordinate grid first (oracle_schedule only produces on-grid d). */
 int64_t oracle_shift_cells(const oracle_geom *g, float *disk, int16_t *n, int f, float d);
 
 /* a18: host randomness start.cu:238,251-252 made deterministic from (seed, sweep). */
@@ -90,6 +120,8 @@ int64_t oracle_sweep(const oracle_geom *g, float *disk, int16_t *n,
 int oracle_sweep_omp(const oracle_geom *g, float *disk, int16_t *n,
                      uint64_t sweep0, int n_sweeps,
                      uint64_t *trials, uint64_t *accepted, int64_t *lost);
+
+int oracle_set_threads(int n);   /* OpenMP threads of oracle_sweep_omp (n <= 0: query only) */
 
 /* disk/n -> global coordinates in reference layout order (disk_to_r kernel.cu:497-507). */
 int64_t oracle_disk_to_r(const oracle_geom *g, const float *disk, const int16_t *n, float *r);

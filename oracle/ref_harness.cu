@@ -13,7 +13,10 @@
 // n_real .. 799 are parked at x = 1000, outside every cell: the reference's membership test
 // (kernel.cu:134) drops them.
 //
-// usage: ref_harness <seed> <n_real>   (JSON on stdout; GPU required)
+// usage: ref_harness <seed> <n_real> [n_crowd]   (JSON on stdout; GPU required)
+// n_crowd > 0: the first n_crowd particles (after the six face probes) alternate between cells (1,1) and
+// (2,1), so that cells hold 7-8 particles and shiftCells moves several particles between two crowded
+// cells (our nmax is 8, the reference's 30: the tests compare the first 8 slots and the overflow count).
 #define main pmc_ref_kernel_cu_main
 #include REF_KERNEL_CU
 #undef main
@@ -55,6 +58,7 @@ int main(int argc, char **argv)
 {
     const uint64_t seed = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
     const int n_real = argc > 2 ? atoi(argv[2]) : 40;
+    const int n_crowd = argc > 3 ? atoi(argv[3]) : 0;
     lcg_state = seed * 2654435761ull + 12345ull;
 
     std::vector<float> r(3 * N_ATOMS);
@@ -66,6 +70,12 @@ int main(int argc, char **argv)
         } else {
             r[i] = 1000.0f; r[i + N_ATOMS] = 1000.0f; r[i + 2 * N_ATOMS] = 1000.0f;
         }
+    }
+    for (int k = 0; k < n_crowd && 6 + k < n_real; k++) {
+        const int i = 6 + k;
+        const float x0 = (k & 1) ? 0.0f : -2.5f;                    // lower face of cell column 2 / 1
+        r[i] = x0 + (float)(1 + (int)(lcg() % 2560u)) / 1024.0f;     // (x0, x0 + 2.5]
+        r[i + N_ATOMS] = -2.5f + (float)(1 + (int)(lcg() % 2560u)) / 1024.0f;   // cell row 1
     }
     // edge cases of the half-open rule lb < x <= ub (kernel.cu:134): exactly on cell faces,
     // on the upper box face (kept) and on the lower box face (dropped)
@@ -88,8 +98,8 @@ int main(int argc, char **argv)
     std::vector<short> n(CPS3);
 
     printf("{\"source\": \"reference kernels assign (kernel.cu:92-150) and shiftCells (V2 shiftCells.h:23-112), run unmodified on a B200\",\n");
-    printf(" \"params\": {\"N_ATOMS\": %d, \"L\": %.9g, \"cellsPerSide\": %d, \"w\": %.9g, \"nmax\": %d, \"seed\": %llu, \"n_real\": %d},\n",
-           N_ATOMS, (float)L, cellsPerSide, (float)w, nmax, (unsigned long long)seed, n_real);
+    printf(" \"params\": {\"N_ATOMS\": %d, \"L\": %.9g, \"cellsPerSide\": %d, \"w\": %.9g, \"nmax\": %d, \"seed\": %llu, \"n_real\": %d, \"n_crowd\": %d},\n",
+           N_ATOMS, (float)L, cellsPerSide, (float)w, nmax, (unsigned long long)seed, n_real, n_crowd);
     printf(" \"r\": [");
     for (int dim = 0; dim < 3; dim++) {
         printf("[");

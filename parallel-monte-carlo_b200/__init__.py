@@ -45,7 +45,7 @@ class Geometry(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("cps", C.c_int), ("n_cells", C.c_int64),
                 ("nmax", C.c_int), ("n_M", C.c_int), ("w", C.c_float), ("L", C.c_float),
                 ("sigma_d", C.c_float), ("move_delta", C.c_float), ("row0", C.c_int),
-                ("rows", C.c_int), ("ghost_rows", C.c_int), ("local_cells", C.c_int64)]
+                ("rows", C.c_int), ("ghost_rows", C.c_int), ("local_cells", C.c_int64), ("grid_q", C.c_float)]
 
 
 def _stale():

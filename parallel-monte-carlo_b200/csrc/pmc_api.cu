@@ -100,15 +100,37 @@ struct pmc_handle {
     unsigned *v4_flags[2];
     unsigned v4_epoch[2], v4_epoch_next;
     long long launches;         // kernels launched by this handle since the last pmc_reset_counters
+    // result-invariant tuning knobs (pmc_set_tuning)
+    int tune_bands, tune_prefetch, tune_overlap, tune_generic, tune_force;
+    unsigned status_sticky;     // status bits already handed to the caller as a return code (pmc_get_counters ORs them back in)
+    Counters *h_ctr;            // pinned host mirror for the status read of blocking calls
     alignas(64) unsigned char v4_tmap[2][2][128];   // [buffer][0: full-tile box, 1: half-height box]
 };
 
+// every entry point runs on the handle's device and leaves the caller's current device as it found it
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); }
+    ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define GUARD(h) DevGuard guard_((h)->device)
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
+// Blocking calls end here: synchronise, then turn a cell overflow / lost particles that happened since the
+// last check into the return code pmc.h promises (the reference writes past nmax silently).  The arrays are
+// still complete and consistent except for the dropped particles; the counters keep the totals.  Non-blocking
+// callers poll pmc_get_counters.
 static int finish(pmc_handle *h)
 {
-    if (h->blocking) CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    if (!h->blocking) return 0;
+    CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const unsigned st = h->h_ctr->status;
+    if (!st) return 0;
+    CK(cudaMemsetAsync(&h->d_ctr->status, 0, sizeof(unsigned), h->stream));     // reported once; sticky on the host
+    h->status_sticky |= st;
+    return (st & PMC_STATUS_OVERFLOW) ? PMC_E_OVERFLOW : PMC_E_LOST;
 }
 
 static void host_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t out[4])
@@ -130,6 +152,11 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     if (p.n_particles <= 0 || !(p.phi > 0.0f) || !(p.sigma_d > 0.0f) || !(p.cell_w >= p.sigma_d) ||
         p.n_M < 1 || p.n_M > 64 || !(p.move_delta > 0.0f)) return PMC_E_INVALID;
     if (p.nmax != PMC_NMAX) return PMC_E_UNSUPPORTED;
+    // a cell of width w holds pi/4 * w^2 * phi / (pi sigma^2 / 4) disks on average; with less than two slots
+    // of head-room above that mean, overflow is the rule rather than a 1e-5 event (cell_w = 3 sigma at
+    // phi = 0.7: mean 8.0).  Overflow at run time is still detected and reported (PMC_E_OVERFLOW).
+    if ((double)p.phi * (double)p.cell_w * (double)p.cell_w * 4.0 / (M_PI * (double)p.sigma_d * (double)p.sigma_d) > PMC_NMAX - 2)
+        return PMC_E_UNSUPPORTED;
     if (p.cps_multiple < 2) p.cps_multiple = 2;
     if (p.cps_multiple & 1) return PMC_E_INVALID;
     if (p.n_ranks < 1) p.n_ranks = 1;
@@ -138,16 +165,23 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     long long cps = (long long)floor(L_d / ((double)p.cps_multiple * (double)p.cell_w)) * p.cps_multiple;
     if (cps < 4 || cps > 46340) return PMC_E_INVALID;
     double w_d = L_d / (double)cps;
+    // coordinate grid (pmc.h): q = 2^e with every multiple of q below 2^(e+24) > 2w representable
+    int ex;
+    (void)frexp(2.0 * w_d, &ex);
+    const double q = ldexp(1.0, ex - 24);
+    const double K = nearbyint(w_d / q), M = floor((double)p.move_delta / q);
+    if (M < 1.0 || M >= 4194304.0 || (double)p.move_delta > w_d) return PMC_E_INVALID;
     DevGeom g;
     memset(&g, 0, sizeof(g));
     g.cps = (int)cps;
-    g.w = (float)w_d;
+    g.w = (float)(K * q);
+    g.K = (int)K; g.M = (int)M; g.nM2 = 2u * (unsigned)M + 1u; g.mofs = (float)(8388608.0 + M);
     g.L_box = (double)cps * (double)g.w;
     g.L = (float)g.L_box;
     g.half_L = g.L / 2.0f;
     g.sigma = p.sigma_d;
     g.sigma2 = p.sigma_d * p.sigma_d;
-    g.dscale = p.move_delta * 1.1920928955078125e-07f;     // 2^-23
+    g.dscale = (float)q;
     g.n_M = p.n_M;
     g.seed_lo = (unsigned)p.seed;
     g.seed_hi = (unsigned)(p.seed >> 32);
@@ -167,7 +201,7 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     pmc_geometry pg;
     memset(&pg, 0, sizeof(pg));
     pg.n_particles = p.n_particles; pg.cps = g.cps; pg.n_cells = cps * cps; pg.nmax = PMC_NMAX;
-    pg.n_M = p.n_M; pg.w = g.w; pg.L = g.L; pg.sigma_d = p.sigma_d; pg.move_delta = p.move_delta;
+    pg.n_M = p.n_M; pg.w = g.w; pg.L = g.L; pg.sigma_d = p.sigma_d; pg.move_delta = (float)(M * q); pg.grid_q = (float)q;
     pg.row0 = g.row0; pg.rows = g.rows; pg.ghost_rows = g.ghost;
     pg.local_cells = (long long)g.local_rows * g.cps;
     if (p_out) *p_out = p;
@@ -206,8 +240,10 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
     pmc_geometry pg0;
     int grc = derive_geometry(*pp, &p, &g0, &pg0);
     if (grc) return grc;
-    pmc_handle *h = (pmc_handle *)calloc(1, sizeof(pmc_handle));
+    // the handle embeds CUtensorMap storage: 64-byte alignment (calloc guarantees 16)
+    pmc_handle *h = (pmc_handle *)aligned_alloc(64, (sizeof(pmc_handle) + 63) / 64 * 64);
     if (!h) return PMC_E_INVALID;
+    memset(h, 0, sizeof(pmc_handle));
     h->p = p;
     h->g = g0;
     h->pg = pg0;
@@ -217,18 +253,24 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
         Geom4 &q = h->g4;
         q.cps = g.cps; q.row0 = g.row0; q.rows = g.rows; q.wrap_y = g.wrap_y;
         pmc4_alloc_shape(g.cps, g.rows, &q.CH, &q.ROWS, &q.FW, &q.FH);
-        q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale;
+        q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale; q.nM2 = g.nM2; q.mofs = g.mofs;
         q.seed_lo = g.seed_lo; q.seed_hi = g.seed_hi;
         q.try_ns4 = (double)p.n_particles / ((double)g.cps * (double)g.cps) < 2.5;   // a performance hint only
         for (int r = 0; r < 10; r++) { q.pk0[r] = g.seed_lo + (unsigned)r * 0x9E3779B9u; q.pk1[r] = g.seed_hi + (unsigned)r * 0xBB67AE85u; }
         h->v4_ok = (p.n_M == 4) && ((double)g.w >= 2.0 * (double)p.sigma_d * (1.0 + 1e-5)) && g.cps >= 48 &&
                    g.rows >= 2 * kMY && (p.n_ranks == 1 || kGhostRows == kMY);
-        const char *force = getenv("PMC_FORCE_GENERIC");
-        if (force && atoi(force)) h->v4_ok = 0;
     }
+    // tuning defaults; PMC_BANDS / PMC_PREFETCH remain as documented environment overrides of the two
+    // performance knobs (they cannot change results)
+    h->tune_bands = [] { const char *e = getenv("PMC_BANDS"); return e ? atoi(e) : 6; }();
+    h->tune_prefetch = [] { const char *e = getenv("PMC_PREFETCH"); return e ? atoi(e) : 296; }();
+    h->tune_overlap = 1;
+    int caller_dev = -1;
+    cudaGetDevice(&caller_dev);
     if (p.device >= 0) { cudaError_t e = cudaSetDevice(p.device); if (e != cudaSuccess) { free(h); return (int)e; } }
     cudaError_t e = cudaGetDevice(&h->device);
     if (e != cudaSuccess) { free(h); return (int)e; }
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore_{ caller_dev };
     {   // stream-ordered scratch (cell-list build) stays cached in the device's default pool
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
@@ -244,6 +286,7 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
     if (e == cudaSuccess) e = cudaMemset(h->d_ctr, 0, sizeof(Counters));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_out4, 4 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_min, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctr, sizeof(Counters));
     if (e != cudaSuccess) { pmc_destroy(h); return (int)e; }
     *out = h;
     return 0;
@@ -252,8 +295,10 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
 int pmc_destroy(pmc_handle *h)
 {
     if (!h) return PMC_E_INVALID;
-    cudaStreamSynchronize(h->stream);
+    GUARD(h);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
     cudaFree(h->d_ctr); cudaFree(h->scratch_disk); cudaFree(h->scratch_n);
     cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
     cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
@@ -273,9 +318,29 @@ int pmc_destroy(pmc_handle *h)
         cudaStreamDestroy(h->comm_stream);
         for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_interior[b]); cudaEventDestroy(h->ev_exchanged[b]); }
     }
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     free(h);
     return 0;
+}
+
+// Result-invariant knobs: which kernel / schedule computes the (identical) result.
+//   "bands" (1..8)        tile-row bands of a sweep on their own streams (default 6)
+//   "prefetch" (>= 0)     L2 prefetch distance in CTAs (default 296)
+//   "overlap" (0/1)       slab runs: boundary rows + NCCL ring on a side stream (default 1)
+//   "generic" (0/1)       use the generic fused kernel (pmc_sweep.cu) even where the fast path qualifies
+//   "force_crowded", "no_ns4", "full_halo" (0/1)   drive the rare paths of the fast kernel on ordinary tiles
+int pmc_set_tuning(pmc_handle *h, const char *name, int value)
+{
+    if (!h || !name) return PMC_E_INVALID;
+    auto flag = [&](int bit) { h->tune_force = value ? (h->tune_force | bit) : (h->tune_force & ~bit); return 0; };
+    if (!strcmp(name, "bands")) { if (value < 1 || value > kMaxBands) return PMC_E_INVALID; h->tune_bands = value; return 0; }
+    if (!strcmp(name, "prefetch")) { if (value < 0) return PMC_E_INVALID; h->tune_prefetch = value; return 0; }
+    if (!strcmp(name, "overlap")) { h->tune_overlap = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "generic")) { h->tune_generic = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "force_crowded")) return flag(8);
+    if (!strcmp(name, "no_ns4")) return flag(16);
+    if (!strcmp(name, "full_halo")) return flag(64);
+    return PMC_E_INVALID;
 }
 
 int pmc_get_geometry(const pmc_handle *h, pmc_geometry *g)
@@ -292,6 +357,7 @@ size_t pmc_n_bytes(const pmc_handle *h) { return h ? (size_t)h->pg.local_cells *
 int pmc_set_stream(pmc_handle *h, void *cuda_stream)
 {
     if (!h) return PMC_E_INVALID;
+    GUARD(h);
     CK(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
     h->stream = (cudaStream_t)cuda_stream;
@@ -308,6 +374,7 @@ int pmc_set_blocking(pmc_handle *h, int blocking)
 int pmc_synchronize(pmc_handle *h)
 {
     if (!h) return PMC_E_INVALID;
+    GUARD(h);
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -316,6 +383,7 @@ int pmc_synchronize(pmc_handle *h)
 int pmc_init_r(pmc_handle *h, float *d_r)
 {
     if (!h || !d_r) return PMC_E_INVALID;
+    GUARD(h);
     long long N = h->p.n_particles;
     long long ns = (long long)floor(sqrt((double)N) + 0.5);
     if (ns * ns != N) return PMC_E_NOT_SQUARE;
@@ -326,6 +394,7 @@ int pmc_init_r(pmc_handle *h, float *d_r)
 int pmc_assign(pmc_handle *h, const float *d_r, float *d_disk, int16_t *d_n)
 {
     if (!h || !d_r || !d_disk || !d_n) return PMC_E_INVALID;
+    GUARD(h);
     CK(pmc_launch_assign(h->g, d_r, (float4 *)d_disk, d_n, h->d_ctr, h->stream)); h->launches += 2;
     return finish(h);
 }
@@ -369,9 +438,10 @@ int pmc_schedule(const pmc_handle *h, uint64_t sweep, int order[4], int *f, floa
         int t = order[i]; order[i] = order[j]; order[j] = t;
     }
     *f = (int)(a[3] >> 31);                             // kernel.cu:683 range, 2 axes
-    volatile float u = (float)((b[0] >> 8) + 1u) * 5.9604644775390625e-08f;
-    volatile float um = u - 0.5f;
-    *d = um * h->g.w;                                   // kernel.cu:684: (-w/2, w/2]
+    // kernel.cu:684 range (-w/2, w/2], on the coordinate grid: dk * q (oracle_schedule)
+    const int64_t K = h->g.K;
+    const int64_t dk = (int64_t)(((uint64_t)b[0] * (uint64_t)K) >> 32) + 1 - (K + 1) / 2;
+    *d = (float)dk * h->g.dscale;
     return 0;
 }
 
@@ -409,6 +479,7 @@ static int exchange_ghosts_async(pmc_handle *h, float4 *disk, int16_t *n)
 int pmc_subsweep(pmc_handle *h, float *d_disk, int16_t *d_n, const int off[2], uint64_t sweep)
 {
     if (!h || !d_disk || !d_n || !off) return PMC_E_INVALID;
+    GUARD(h);
     if ((off[0] | off[1]) & ~1) return PMC_E_INVALID;
     SweepArgs a;
     memset(&a, 0, sizeof(a));
@@ -425,7 +496,9 @@ int pmc_subsweep(pmc_handle *h, float *d_disk, int16_t *d_n, const int off[2], u
 int pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
 {
     if (!h || !d_disk || !d_n || f < 0 || f > 1) return PMC_E_INVALID;
+    GUARD(h);
     if (!(fabsf(d) <= 0.5f * h->g.w * 1.0001f)) return PMC_E_INVALID;   // shiftCells.h:7 contract
+    d = (float)(nearbyint((double)d / (double)h->g.dscale) * (double)h->g.dscale);   // onto the coordinate grid
     int rc = ensure_scratch(h);
     if (rc) return rc;
     CK(pmc_launch_shift(h->g, (const float4 *)d_disk, d_n, h->scratch_disk, h->scratch_n, f, d, h->d_ctr, h->stream)); h->launches += 1;
@@ -492,9 +565,14 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         h->v4_padded = 1;
     }
     int cur = 0;
-    static const int dbg = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
-    static const int overlap = [] { const char *e = getenv("PMC_OVERLAP"); return e ? atoi(e) : 1; }();
-    static const int fast_ok = [] { const char *e = getenv("PMC_FAST"); return e ? atoi(e) : 1; }();
+#ifdef PMC_DEBUG
+    static const int dbg_env = [] { const char *e = getenv("PMC_DBG_SKIP"); return e ? atoi(e) : 0; }();
+#else
+    const int dbg_env = 0;
+#endif
+    const int dbg = (h->tune_force & kTuneForceBits) | dbg_env;
+    const int overlap = h->tune_overlap;
+    const int fast_ok = 1;
     if (h->p.n_ranks > 1 && !h->comm_stream) {
         int prio_lo = 0, prio_hi = 0;               // the exchange must not queue behind the interior tiles
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -504,17 +582,22 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
             CK(cudaEventCreateWithFlags(&h->ev_exchanged[b], cudaEventDisableTiming));
         }
     }
-    static const int pf_ahead = [] { const char *e = getenv("PMC_PREFETCH"); return e ? atoi(e) : 296; }();
-    cudaEvent_t k0, k1;
-    CK(cudaEventCreate(&k0));
-    CK(cudaEventCreate(&k1));
+    const int pf_ahead = h->tune_prefetch;
+    // the event pair that times the sweep kernels of this call; owned by this scope until it is queued
+    struct EvPair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EvPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } kev;
+    CK(cudaEventCreate(&kev.a));
+    CK(cudaEventCreate(&kev.b));
+    cudaEvent_t k0 = kev.a, k1 = kev.b;
     CK(cudaEventRecord(k0, h->stream));
     int slab_split = 0, last_split_par = 0;         // the previous sweep ran on two streams
     // Single GPU: the tile rows of a sweep are cut into `bands` bands, each on its own stream.  Band b of
     // sweep t+1 reads and overwrites only what bands b-1, b, b+1 (periodic) of sweep t wrote and read, so it
     // waits for those three alone: the last CTAs of sweep t and the first of t+1 share the GPU, there is no
     // idle tail and no launch gap between sweeps.
-    static const int bands_env = [] { const char *e = getenv("PMC_BANDS"); return e ? atoi(e) : 6; }();
+    const int bands_env = h->tune_bands;
     // at least 3 tile rows per band whatever this call's sweeps choose as tile height (<= 28 rows), at least
     // 4 bands (with 3, every band is every other band's neighbour); fixed for the whole call
     int bands = (h->g4.rows + 27) / 28 / 3;
@@ -572,6 +655,10 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
             const int par = t & 1;
             const bool first_split = !slab_split;
             const bool sb = sbands > 1;              // interior in bands: the same for every sweep of a call
+            // what makes the event graph below race-free: a band reads / overwrites rows of its two neighbour
+            // bands only, i.e. every band holds at least 3 tile rows and its edges move by less than one tile row
+            // (the halo, <= 5 rows, plus the change of tile height between consecutive sweeps, <= 4 rows)
+            if (sb && top0 - 1 < 3 * sbands) return PMC_E_INVALID;
             if (first_split) {                       // first split sweep of this call: everything so far is on the main stream
                 CK(cudaEventRecord(sb ? h->ev_band_start : h->ev_interior[par ^ 1], h->stream));
                 slab_split = 1;
@@ -643,6 +730,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     CK(cudaEventRecord(k1, h->stream));
     if (!h->ktime_pending) h->ktime_pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
     h->ktime_pending->push_back(std::make_pair(k0, k1));
+    kev.a = kev.b = nullptr;                        // now owned by the pending list
     h->ktime_pending_launches += n_sweeps;
     if (h->ktime_pending->size() > 4096) { double ms; long long nl; pmc_get_kernel_time(h, &ms, &nl); }
     CK(pmc4_launch_export(h->g4, ghost, h->v4_buf[cur], (float4 *)d_disk, d_n, h->stream)); h->launches += 1;
@@ -655,8 +743,9 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
 int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n_sweeps)
 {
     if (!h || !d_disk || !d_n || n_sweeps < 0) return PMC_E_INVALID;
+    GUARD(h);
     if (n_sweeps == 0) return 0;
-    if (h->v4_ok) return sweep_v4(h, d_disk, d_n, sweep0, n_sweeps);
+    if (h->v4_ok && !h->tune_generic) return sweep_v4(h, d_disk, d_n, sweep0, n_sweeps);
     int rc = ensure_scratch(h);
     if (rc) return rc;
     float4 *cur_d = (float4 *)d_disk, *oth_d = h->scratch_disk;
@@ -679,7 +768,9 @@ int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n
         a.sweep_lo = (unsigned)sweep; a.sweep_hi = (unsigned)(sweep >> 32);
         a.shift_on = pend_on; a.shift_f = pend_f; a.shift_d = pend_d;
         a.sanitize_in = (t == 0);       // only the first kernel reads the caller's arrays
+#ifdef PMC_DEBUG
         { const char *dbg = getenv("PMC_DBG_SKIP"); a.dbg_skip = dbg ? atoi(dbg) : 0; }
+#endif
         CK(pmc_launch_fused_sweep(h->g, cur_d, cur_n, oth_d, oth_n, a, h->d_ctr, h->stream)); h->launches += 1;
         rc = exchange_ghosts_async(h, oth_d, oth_n);
         if (rc) return rc;
@@ -701,13 +792,14 @@ int pmc_sweep(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0, int n
 int pmc_get_counters(pmc_handle *h, uint64_t *trials, uint64_t *accepted, uint64_t *lost, uint32_t *status)
 {
     if (!h) return PMC_E_INVALID;
+    GUARD(h);
     Counters c;
     CK(cudaMemcpyAsync(&c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (trials) *trials = c.trials;
     if (accepted) *accepted = c.accepted;
     if (lost) *lost = c.lost;
-    if (status) *status = c.status;
+    if (status) *status = c.status | h->status_sticky;
     return 0;
 }
 
@@ -716,6 +808,7 @@ int pmc_get_counters(pmc_handle *h, uint64_t *trials, uint64_t *accepted, uint64
 int pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launches)
 {
     if (!h) return PMC_E_INVALID;
+    GUARD(h);
     if (h->ktime_pending && !h->ktime_pending->empty()) {
         CK(cudaStreamSynchronize(h->stream));
         for (auto &pr : *h->ktime_pending) {
@@ -743,15 +836,19 @@ int pmc_get_launch_count(pmc_handle *h, long long *launches)
 int pmc_reset_counters(pmc_handle *h)
 {
     if (!h) return PMC_E_INVALID;
+    GUARD(h);
     h->launches = 0;
+    h->status_sticky = 0;
     { double ms; long long nl; pmc_get_kernel_time(h, &ms, &nl); h->ktime_ms = 0.0; h->ktime_launches = 0; }
     CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
-    return finish(h);
+    if (h->blocking) CK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int pmc_check(pmc_handle *h, const float *d_disk, const int16_t *d_n, int64_t out[4], float *min_d2)
 {
     if (!h || !d_disk || !d_n || !out || !min_d2) return PMC_E_INVALID;
+    GUARD(h);
     CK(pmc_launch_check(h->g, (const float4 *)d_disk, d_n, h->d_out4, h->d_min, h->stream)); h->launches += 1;
     long long o[4];
     unsigned bits;
@@ -768,6 +865,7 @@ int pmc_check(pmc_handle *h, const float *d_disk, const int16_t *d_n, int64_t ou
 int pmc_gr_hist(pmc_handle *h, const float *d_disk, const int16_t *d_n, float r_max, int nbins, uint64_t *hist_host)
 {
     if (!h || !d_disk || !d_n || !hist_host || nbins < 1 || nbins > 4096) return PMC_E_INVALID;
+    GUARD(h);
     if (!(r_max > 0.0f) || r_max > h->g.w) return PMC_E_INVALID;
     if (h->hist_cap < nbins) {
         cudaFree(h->d_hist); h->d_hist = nullptr; h->hist_cap = 0;
@@ -824,41 +922,59 @@ int pmc_pressure_from_hist(const pmc_handle *h, const uint64_t *hist, float r_ma
     return 0;
 }
 
-// ------------------------------------------------------------------ host I/O
+// ------------------------------------------------------------------ results back in the reference's order
+// disk_to_r kernel.cu:497-507 on the device: d_r is SoA [2][N] global coordinates, cells in order, slots in
+// order (owned rows only; a slab writes its own particles from index 0).  *n_found = particles met.
+int pmc_disk_to_r(pmc_handle *h, const float *d_disk, const int16_t *d_n, float *d_r, int64_t *n_found)
+{
+    if (!h || !d_disk || !d_n || !d_r) return PMC_E_INVALID;
+    GUARD(h);
+    unsigned long long *scratch = nullptr;
+    int nblocks = 0;
+    CK(pmc_launch_disk_to_r(h->g, (const float4 *)d_disk, d_n, d_r, h->p.n_particles, h->p.n_particles, &scratch, &nblocks, h->stream));
+    h->launches += 3;
+    unsigned long long total = 0;
+    cudaError_t e = cudaMemcpyAsync(&total, scratch + nblocks, sizeof(total), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFreeAsync(scratch, h->stream);
+    if (e != cudaSuccess) return (int)e;
+    if (n_found) *n_found = (int64_t)total;
+    return 0;
+}
+
+// the same into HOST memory (start.cu:261-263 copies the cells back and prints them): converted on the device,
+// then one D2H copy per coordinate through a pinned staging buffer
 int pmc_disk_to_r_host(pmc_handle *h, const float *d_disk, const int16_t *d_n, float *r_host, int64_t *n_found)
 {
     if (!h || !d_disk || !d_n || !r_host) return PMC_E_INVALID;
-    const DevGeom &g = h->g;
-    size_t db = pmc_disk_bytes(h), nb = pmc_n_bytes(h);
-    std::vector<float> disk(db / sizeof(float));
-    std::vector<int16_t> n(nb / sizeof(int16_t));
-    CK(cudaMemcpyAsync(disk.data(), d_disk, db, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(n.data(), d_n, nb, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    // disk_to_r kernel.cu:497-507: cells in order, slots in order (owned rows only)
+    GUARD(h);
     const long long N = h->p.n_particles;
-    long long k = 0;
-    for (int lr = g.ghost; lr < g.ghost + g.rows; lr++) {
-        int cy = g.row0 + (lr - g.ghost);
-        for (int cx = 0; cx < g.cps; cx++) {
-            long long c = (long long)lr * g.cps + cx;
-            double ox = (double)cx * (double)g.w - g.L_box * 0.5, oy = (double)cy * (double)g.w - g.L_box * 0.5;
-            for (int s = 0; s < n[c]; s++) {
-                if (k < N) {
-                    r_host[k] = (float)(ox + (double)disk[c * 16 + s]);
-                    r_host[k + N] = (float)(oy + (double)disk[c * 16 + 8 + s]);
-                }
-                k++;
-            }
+    float *d_r = nullptr;
+    CK(cudaMallocAsync(&d_r, (size_t)2 * N * sizeof(float), h->stream));
+    int64_t found = 0;
+    int rc = pmc_disk_to_r(h, d_disk, d_n, d_r, &found);
+    if (!rc) {
+        const size_t chunk = (size_t)8 << 20;       // floats per staged piece (32 MB pinned)
+        float *stage = nullptr;
+        cudaError_t e = cudaMallocHost(&stage, chunk * sizeof(float));
+        for (size_t o = 0; e == cudaSuccess && o < (size_t)2 * N; o += chunk) {
+            const size_t m = (size_t)2 * N - o < chunk ? (size_t)2 * N - o : chunk;
+            e = cudaMemcpyAsync(stage, d_r + o, m * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e == cudaSuccess) memcpy(r_host + o, stage, m * sizeof(float));
         }
+        if (stage) cudaFreeHost(stage);
+        if (e != cudaSuccess) rc = (int)e;
     }
-    if (n_found) *n_found = k;
-    return 0;
+    cudaFreeAsync(d_r, h->stream);
+    if (n_found) *n_found = found;
+    return rc;
 }
 
 int pmc_run_host(pmc_handle *h, const float *r_host, uint64_t sweep0, int n_sweeps, float *disk_host, int16_t *n_host)
 {
     if (!h || !r_host || !disk_host || !n_host) return PMC_E_INVALID;
+    GUARD(h);
     if (!h->run_r) CK(cudaMalloc(&h->run_r, pmc_r_bytes(h)));
     if (!h->run_disk) CK(cudaMalloc(&h->run_disk, pmc_disk_bytes(h)));
     if (!h->run_n) CK(cudaMalloc(&h->run_n, pmc_n_bytes(h)));
@@ -871,8 +987,10 @@ int pmc_run_host(pmc_handle *h, const float *r_host, uint64_t sweep0, int n_swee
     if (rc) return rc;
     CK(cudaMemcpyAsync(disk_host, h->run_disk, pmc_disk_bytes(h), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(n_host, h->run_n, pmc_n_bytes(h), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    h->blocking = 1;
+    rc = finish(h);                                 // synchronises; overflow / lost particles become the return code
+    h->blocking = was_blocking;
+    return rc;
 }
 
 // ------------------------------------------------------------------ initial configurations / trajectory / checkpoint
@@ -954,62 +1072,96 @@ int pmc_write_dump(pmc_handle *h, const float *d_disk, const int16_t *d_n, const
     return 0;
 }
 
-// Binary checkpoint / restart of (params, sweep, counters, disk, n): the reference has none
-// (SURVEY section 5); needed for long equation-of-state runs.
-struct CkptHeader {
-    char magic[8];
-    uint32_t version, nmax;
-    pmc_params params;
-    uint64_t sweep, trials, accepted, lost;
-    uint64_t disk_bytes, n_bytes;
+// Binary checkpoint / restart of (params, sweep, counters, status, disk, n): the reference has none
+// (SURVEY section 5); needed for long equation-of-state runs.  The header is written field by field as
+// little-endian fixed-width integers / IEEE bit patterns (no struct padding, no compiler dependence).
+namespace {
+constexpr uint32_t kCkptVersion = 2;
+struct CkptWriter {
+    std::vector<unsigned char> b;
+    void u32(uint32_t v) { for (int i = 0; i < 4; i++) b.push_back((unsigned char)(v >> (8 * i))); }
+    void u64(uint64_t v) { for (int i = 0; i < 8; i++) b.push_back((unsigned char)(v >> (8 * i))); }
+    void f32(float f) { uint32_t v; memcpy(&v, &f, 4); u32(v); }
 };
+struct CkptReader {
+    const unsigned char *p, *end;
+    bool ok = true;
+    uint32_t u32() { if (end - p < 4) { ok = false; return 0; } uint32_t v = 0; for (int i = 0; i < 4; i++) v |= (uint32_t)p[i] << (8 * i); p += 4; return v; }
+    uint64_t u64() { if (end - p < 8) { ok = false; return 0; } uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i); p += 8; return v; }
+    float f32() { uint32_t v = u32(); float f; memcpy(&f, &v, 4); return f; }
+};
+constexpr size_t kCkptHeaderBytes = 8 + 4 * 2 + 8 + 4 * 3 + 4 * 2 + 4 + 8 + 4 * 3 + 8 * 4 + 4 + 8 * 2;   // 120
+}  // namespace
 
 int pmc_save_checkpoint(pmc_handle *h, const float *d_disk, const int16_t *d_n, uint64_t sweep, const char *path)
 {
     if (!h || !d_disk || !d_n || !path) return PMC_E_INVALID;
-    CkptHeader hd;
-    memset(&hd, 0, sizeof(hd));
-    memcpy(hd.magic, "PMCB200", 8);
-    hd.version = 1; hd.nmax = PMC_NMAX; hd.params = h->p; hd.sweep = sweep;
+    GUARD(h);
+    uint64_t trials, accepted, lost;
     uint32_t status;
-    int rc = pmc_get_counters(h, &hd.trials, &hd.accepted, &hd.lost, &status);
+    int rc = pmc_get_counters(h, &trials, &accepted, &lost, &status);
     if (rc) return rc;
-    hd.disk_bytes = pmc_disk_bytes(h); hd.n_bytes = pmc_n_bytes(h);
-    std::vector<char> buf(hd.disk_bytes + hd.n_bytes);
-    CK(cudaMemcpyAsync(buf.data(), d_disk, hd.disk_bytes, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(buf.data() + hd.disk_bytes, d_n, hd.n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    const pmc_params &p = h->p;
+    CkptWriter wr;
+    for (int i = 0; i < 8; i++) wr.b.push_back((unsigned char)"PMCB200"[i]);
+    wr.u32(kCkptVersion); wr.u32(PMC_NMAX);
+    wr.u64((uint64_t)p.n_particles); wr.f32(p.phi); wr.f32(p.sigma_d); wr.f32(p.cell_w);
+    wr.u32((uint32_t)p.nmax); wr.u32((uint32_t)p.n_M); wr.f32(p.move_delta); wr.u64(p.seed);
+    wr.u32((uint32_t)p.cps_multiple); wr.u32((uint32_t)p.rank); wr.u32((uint32_t)p.n_ranks);
+    wr.u64(sweep); wr.u64(trials); wr.u64(accepted); wr.u64(lost); wr.u32(status);
+    const uint64_t disk_bytes = pmc_disk_bytes(h), n_bytes = pmc_n_bytes(h);
+    wr.u64(disk_bytes); wr.u64(n_bytes);
+    if (wr.b.size() != kCkptHeaderBytes) return PMC_E_INVALID;
+    std::vector<char> buf(disk_bytes + n_bytes);
+    CK(cudaMemcpyAsync(buf.data(), d_disk, disk_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(buf.data() + disk_bytes, d_n, n_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     FILE *fp = fopen(path, "wb");
     if (!fp) return PMC_E_INVALID;
-    bool ok = fwrite(&hd, sizeof(hd), 1, fp) == 1 && fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
+    bool ok = fwrite(wr.b.data(), 1, wr.b.size(), fp) == wr.b.size() && fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
     ok = (fclose(fp) == 0) && ok;
     return ok ? 0 : PMC_E_INVALID;
 }
 
+// The state only continues the SAME chain under the geometry, slab layout, move size, trials per sub-sweep
+// and random stream it was written with: every parameter must match (PMC_E_INVALID otherwise).
 int pmc_load_checkpoint(pmc_handle *h, const char *path, float *d_disk, int16_t *d_n, uint64_t *sweep)
 {
     if (!h || !d_disk || !d_n || !path) return PMC_E_INVALID;
+    GUARD(h);
     FILE *fp = fopen(path, "rb");
     if (!fp) return PMC_E_INVALID;
-    CkptHeader hd;
-    if (fread(&hd, sizeof(hd), 1, fp) != 1 || memcmp(hd.magic, "PMCB200", 8) != 0 || hd.version != 1) { fclose(fp); return PMC_E_INVALID; }
-    // the state only makes sense for the geometry and RNG stream it was written with
-    const pmc_params &a = hd.params, &b = h->p;
-    if (a.n_particles != b.n_particles || a.phi != b.phi || a.sigma_d != b.sigma_d || a.cell_w != b.cell_w ||
-        a.nmax != b.nmax || a.cps_multiple != b.cps_multiple || a.rank != b.rank || a.n_ranks != b.n_ranks ||
-        hd.disk_bytes != pmc_disk_bytes(h) || hd.n_bytes != pmc_n_bytes(h)) { fclose(fp); return PMC_E_INVALID; }
-    std::vector<char> buf(hd.disk_bytes + hd.n_bytes);
+    unsigned char hd[kCkptHeaderBytes];
+    if (fread(hd, 1, sizeof(hd), fp) != sizeof(hd) || memcmp(hd, "PMCB200", 8) != 0) { fclose(fp); return PMC_E_INVALID; }
+    CkptReader rd{ hd + 8, hd + sizeof(hd) };
+    const uint32_t version = rd.u32(), nmax_file = rd.u32();
+    pmc_params a;
+    memset(&a, 0, sizeof(a));
+    a.n_particles = (int64_t)rd.u64(); a.phi = rd.f32(); a.sigma_d = rd.f32(); a.cell_w = rd.f32();
+    a.nmax = (int)rd.u32(); a.n_M = (int)rd.u32(); a.move_delta = rd.f32(); a.seed = rd.u64();
+    a.cps_multiple = (int)rd.u32(); a.rank = (int)rd.u32(); a.n_ranks = (int)rd.u32();
+    const uint64_t sw = rd.u64(), trials = rd.u64(), accepted = rd.u64(), lost = rd.u64();
+    const uint32_t status = rd.u32();
+    const uint64_t disk_bytes = rd.u64(), n_bytes = rd.u64();
+    const pmc_params &b = h->p;
+    if (!rd.ok || version != kCkptVersion || nmax_file != PMC_NMAX ||
+        a.n_particles != b.n_particles || a.phi != b.phi || a.sigma_d != b.sigma_d || a.cell_w != b.cell_w ||
+        a.nmax != b.nmax || a.n_M != b.n_M || a.move_delta != b.move_delta || a.seed != b.seed ||
+        a.cps_multiple != b.cps_multiple || a.rank != b.rank || a.n_ranks != b.n_ranks ||
+        disk_bytes != pmc_disk_bytes(h) || n_bytes != pmc_n_bytes(h)) { fclose(fp); return PMC_E_INVALID; }
+    std::vector<char> buf(disk_bytes + n_bytes);
     bool ok = fread(buf.data(), 1, buf.size(), fp) == buf.size();
     fclose(fp);
     if (!ok) return PMC_E_INVALID;
-    CK(cudaMemcpyAsync(d_disk, buf.data(), hd.disk_bytes, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_n, buf.data() + hd.disk_bytes, hd.n_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_disk, buf.data(), disk_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_n, buf.data() + disk_bytes, n_bytes, cudaMemcpyHostToDevice, h->stream));
     Counters c;
     memset(&c, 0, sizeof(c));
-    c.trials = hd.trials; c.accepted = hd.accepted; c.lost = hd.lost;
+    c.trials = trials; c.accepted = accepted; c.lost = lost;
     CK(cudaMemcpyAsync(h->d_ctr, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (sweep) *sweep = hd.sweep;
+    h->status_sticky = status;                      // already reported to whoever wrote the checkpoint
+    if (sweep) *sweep = sw;
     return 0;
 }
 
@@ -1031,7 +1183,7 @@ int pmc_comm_init(pmc_handle *h, const void *id128)
     if (!nccl_load()) return PMC_E_COMM;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    CK(cudaSetDevice(h->device));
+    GUARD(h);
     if (g_nccl.CommInitRank(&h->comm, h->p.n_ranks, id, h->p.rank)) return PMC_E_COMM;
     return 0;
 }
@@ -1039,6 +1191,7 @@ int pmc_comm_init(pmc_handle *h, const void *id128)
 int pmc_exchange_ghosts(pmc_handle *h, float *d_disk, int16_t *d_n)
 {
     if (!h || !d_disk || !d_n) return PMC_E_INVALID;
+    GUARD(h);
     int rc = exchange_ghosts_async(h, (float4 *)d_disk, d_n);
     if (rc) return rc;
     return finish(h);

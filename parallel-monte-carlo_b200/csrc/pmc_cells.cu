@@ -41,13 +41,15 @@ __device__ __forceinline__ int cell_of(float x, const DevGeom &g)
     return c;
 }
 
+// global -> cell-local, snapped to the coordinate grid: k * q with k in [1, K] (oracle to_local)
 __device__ __forceinline__ float to_local(float x, int c, const DevGeom &g)
 {
-    double origin = __dsub_rn(__dmul_rn((double)c, (double)g.w), __dmul_rn(g.L_box, 0.5));
-    float xl = (float)__dsub_rn((double)x, origin);
-    if (xl > g.w) xl = g.w;
-    if (!(xl > 0.0f)) xl = FLT_MIN;
-    return xl;
+    const double origin = __dsub_rn(__dmul_rn((double)c, (double)g.w), __dmul_rn(g.L_box, 0.5));
+    const double q = (double)g.dscale;
+    double k = rint(__ddiv_rn(__dsub_rn((double)x, origin), q));    // exact scaling by a power of two, ties to even
+    k = fmin(k, (double)g.K);
+    k = fmax(k, 1.0);
+    return (float)__dmul_rn(k, q);
 }
 
 // local storage row of global row gy, or -1 if this rank does not store it
@@ -344,7 +346,122 @@ __global__ void gr_hist_kernel(const float4 *__restrict__ disk, const int16_t *_
         if (sh[b]) atomicAdd(hist + b, (unsigned long long)sh[b]);
 }
 
+// ------------------------------------------------------------------ disk -> r (disk_to_r kernel.cu:497-507)
+// Particles in cell order, slots in order: particle k of the output is the k-th particle met when the owned
+// cells are walked row by row.  Three small kernels: per-block particle counts, an exclusive scan of the block
+// sums (one CTA), then every block scans its own cells again and writes its particles (global coordinates,
+// the same double-precision conversion as oracle_disk_to_r).
+constexpr int kD2RCells = 1024;     // cells per block (4 per thread)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total)
+{
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int base = wid ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__device__ __forceinline__ int owned_count(const int16_t *__restrict__ n, const DevGeom &g, long long q)
+{
+    if (q >= (long long)g.rows * g.cps) return 0;
+    const int c = __ldg(n + q + (long long)g.ghost * g.cps);
+    return c < 0 ? 0 : (c > PMC_NMAX ? PMC_NMAX : c);
+}
+
+__global__ void __launch_bounds__(256) d2r_count_kernel(const int16_t *__restrict__ n, DevGeom g, unsigned long long *block_sums)
+{
+    const long long q0 = (long long)blockIdx.x * kD2RCells + threadIdx.x * 4;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v += owned_count(n, g, q0 + k);
+    int total;
+    block_exclusive_scan(v, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (unsigned long long)total;
+}
+
+// one CTA: exclusive scan of the block sums in place; block_sums[nblocks] = grand total
+__global__ void __launch_bounds__(1024) d2r_scan_kernel(unsigned long long *block_sums, int nblocks)
+{
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const unsigned long long v = i < nblocks ? block_sums[i] : 0ull;
+        // per-block sums are < 2^13: scan them as int, carry the 64-bit running total separately
+        int total;
+        const int ex = block_exclusive_scan((int)v, &total);
+        if (i < nblocks) block_sums[i] = carry + (unsigned long long)ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += (unsigned long long)total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nblocks] = carry;
+}
+
+__global__ void __launch_bounds__(256) d2r_write_kernel(const float4 *__restrict__ disk, const int16_t *__restrict__ n, DevGeom g,
+                                                       const unsigned long long *__restrict__ block_sums, float *__restrict__ r,
+                                                       long long r_stride, long long r_cap)
+{
+    const long long q0 = (long long)blockIdx.x * kD2RCells + threadIdx.x * 4;
+    int cnt[4], v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { cnt[k] = owned_count(n, g, q0 + k); v += cnt[k]; }
+    long long pos = (long long)block_sums[blockIdx.x] + block_exclusive_scan(v, nullptr);
+    const double half = __dmul_rn(g.L_box, 0.5);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (!cnt[k]) continue;
+        const long long q = q0 + k;
+        const int row = (int)(q / g.cps), cx = (int)(q - (long long)row * g.cps), cy = g.row0 + row;
+        const float4 *p = disk + (q + (long long)g.ghost * g.cps) * 4;
+        const float4 x03 = __ldg(p), x47 = __ldg(p + 1), y03 = __ldg(p + 2), y47 = __ldg(p + 3);
+        const float X[8] = { x03.x, x03.y, x03.z, x03.w, x47.x, x47.y, x47.z, x47.w };
+        const float Y[8] = { y03.x, y03.y, y03.z, y03.w, y47.x, y47.y, y47.z, y47.w };
+        const double ox = __dsub_rn(__dmul_rn((double)cx, (double)g.w), half), oy = __dsub_rn(__dmul_rn((double)cy, (double)g.w), half);
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if (s < cnt[k] && pos + s < r_cap) {
+                r[pos + s] = (float)__dadd_rn(ox, (double)X[s]);
+                r[pos + s + r_stride] = (float)__dadd_rn(oy, (double)Y[s]);
+            }
+        pos += cnt[k];
+    }
+}
+
 }  // namespace
+
+// d_r: SoA [2][r_stride] global coordinates of this rank's owned particles (at most r_cap of them are written).
+// *scratch (stream-ordered allocation, the caller frees it with cudaFreeAsync) holds the exclusive block offsets;
+// (*scratch)[*nblocks] = how many particles there are.
+cudaError_t pmc_launch_disk_to_r(const DevGeom &g, const float4 *disk, const int16_t *n, float *d_r, long long r_stride,
+                                 long long r_cap, unsigned long long **scratch, int *nblocks, cudaStream_t st)
+{
+    const long long owned = (long long)g.rows * g.cps;
+    const int blocks = (int)((owned + kD2RCells - 1) / kD2RCells);
+    unsigned long long *sums = nullptr;
+    cudaError_t e = cudaMallocAsync(&sums, (size_t)(blocks + 1) * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    d2r_count_kernel<<<blocks, 256, 0, st>>>(n, g, sums);
+    d2r_scan_kernel<<<1, 1024, 0, st>>>(sums, blocks);
+    d2r_write_kernel<<<blocks, 256, 0, st>>>(disk, n, g, sums, d_r, r_stride, r_cap);
+    e = cudaGetLastError();
+    *scratch = sums;
+    *nblocks = blocks;
+    return e;
+}
 
 cudaError_t pmc_launch_init_r(const DevGeom &g, float *d_r, cudaStream_t st)
 {

@@ -21,7 +21,11 @@ struct DevGeom {
     float w;
     float sigma;
     float sigma2;
-    float dscale;           // move_delta * 2^-23
+    float dscale;           // q: the coordinate grid quantum (a power of two; pmc.h "coordinate grid")
+    int K;                  // w / q: cell width in grid units (< 2^23)
+    int M;                  // move_delta / q: trial displacements are m * q, m in [-M, M]
+    unsigned nM2;           // 2M + 1
+    float mofs;             // 2^23 + M (exact): turns the biased mantissa trick into m
     float L;
     float half_L;
     double L_box;
@@ -63,10 +67,19 @@ struct SweepArgs {
     // lo_x / lo_y, 16-23 / 24-31 chunk offset of the first active cell / of its left neighbour in the staged
     // box (lane part excluded)
     unsigned colour_word[4];
-    int dbg_skip;           // tests / profiling only (env PMC_DBG_SKIP): 1 skip sub-sweeps, 2 skip shift, 4 skip store,
-                            // 8 treat every tile as crowded, 16 never use the 4-slot instantiation, 32 skip the
-                            // crowded-cell flag lookup (timing only), 64 full halo for every colour order
+    // result-invariant path selection (pmc_set_tuning; tests use it to drive the rare paths): 8 treat every tile
+    // as crowded, 16 never use the 4-slot instantiation, 64 full halo for every colour order.
+    // Builds with -DPMC_DEBUG additionally honour the phase-isolation bits (env PMC_DBG_SKIP) that DO change
+    // results: 1 skip sub-sweeps, 2 skip shift, 4 skip store, 32 skip the crowded-cell flag lookup.  They
+    // do not exist in the shipped library.
+    int dbg_skip;
 };
+#ifdef PMC_DEBUG
+#define PMC_DBG_BIT(a, bit) ((a).dbg_skip & (bit))
+#else
+#define PMC_DBG_BIT(a, bit) 0
+#endif
+constexpr int kTuneForceBits = 8 | 16 | 64;
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`)
 cudaError_t pmc_launch_init_r(const DevGeom &g, float *d_r, cudaStream_t st);
@@ -84,6 +97,8 @@ cudaError_t pmc_launch_check(const DevGeom &g, const float4 *disk, const int16_t
                              long long *out4, unsigned *min_d2_bits, cudaStream_t st);
 cudaError_t pmc_launch_gr_hist(const DevGeom &g, const float4 *disk, const int16_t *n,
                                float r_max, int nbins, unsigned long long *hist, cudaStream_t st);
+cudaError_t pmc_launch_disk_to_r(const DevGeom &g, const float4 *disk, const int16_t *n, float *d_r, long long r_stride,
+                                 long long r_cap, unsigned long long **scratch, int *nblocks, cudaStream_t st);
 int pmc_fused_launch_count();   // kernels per fused sweep (for bench gpu_launches)
 
 // ---- fast fused sweep on the handle-owned internal layout (pmc_sweep4.cu)
@@ -93,7 +108,9 @@ struct Geom4 {
     int CH;                     // float4 chunks per (row, plane, parity) run
     int ROWS;                   // allocated rows
     int FW, FH;                 // crowded-cell flag grid: words per row, rows
-    float w, hw, sigma2, dscale;
+    float w, hw, sigma2, dscale;    // dscale = q, the coordinate grid quantum
+    unsigned nM2;                   // 2M + 1 trial displacements per axis (DevGeom)
+    float mofs;                     // 2^23 + M
     unsigned seed_lo, seed_hi;
     int try_ns4;                // mean occupancy is low: worth scanning for tiles whose cells all hold <= 4 disks
     unsigned pk0[10], pk1[10];  // Philox round keys seed + r * (0x9E3779B9, 0xBB67AE85): constant-bank operands
@@ -143,6 +160,18 @@ __device__ __forceinline__ void philox4x32_10_keys(uint32_t c0, uint32_t c1, uin
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// Trial displacement in grid units (make_move subsweep.h:60-71, proposal uniform in the square on
+// the coordinate grid): m = floor((2 r24 + 1) * (2M+1) / 2^25) - M from the top 24 bits r24 of r
+// (exactly symmetric, P(m) == P(-m)), as an exact float and without I2F: (r & ~0xFF) | 0x80 =
+// 128 (2 r24 + 1), and the integer multiplier leaves 2^23 + floor(..) in the mantissa of a float.
+// Identical to oracle/pmc_oracle.c subsweep_cell.
+__device__ __forceinline__ float grid_disp(uint32_t r, unsigned nM2, float mofs)
+{
+    uint32_t tb;
+    asm("mad.hi.u32 %0, %1, %2, 1258291200;" : "=r"(tb) : "r"((r & 0xFFFFFF00u) | 0x80u), "r"(nM2));   // + 0x4B000000
+    return __fadd_rn(__uint_as_float(tb), -mofs);
 }
 
 // ------------------------------------------------------------------ small helpers

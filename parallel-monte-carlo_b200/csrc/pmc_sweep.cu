@@ -149,16 +149,6 @@ __device__ __forceinline__ float cell_min_d2(const float4 *cellp, float npx, flo
     return fminf(fminf(fminf(a.x, a.y), fminf(b.x, b.y)), fminf(fminf(c.x, c.y), fminf(e.x, e.y)));
 }
 
-// odd integer 2k + 1, k = (top 23 bits of r) - 2^22: symmetric, exact in binary32, without I2F
-__device__ __forceinline__ float signed_odd23(uint32_t r)
-{
-    // 2^23 + (r >> 9) as a float straight from the integer multiplier (no shift / mask on the ALU pipe)
-    uint32_t tb;
-    asm("mad.hi.u32 %0, %1, 8388608, 1258291200;" : "=r"(tb) : "r"(r));     // (r * 2^23 >> 32) + 0x4B000000
-    const float k = __fadd_rn(__uint_as_float(tb), -12582912.0f);             // (r >> 9) - 2^22, exact
-    return __fmaf_rn(k, 2.0f, 1.0f);
-}
-
 // d2 of the trial point against two slots held in registers
 __device__ __forceinline__ float2 reg2_d2(float qx0, float qx1, float qy0, float qy1, float2 npx, float2 npy)
 {
@@ -185,7 +175,7 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
     const bool small = cps < (RX > RY ? RX : RY) + 2;   // region may wrap more than once
 
     // pending shiftCells(f, d) of the previous sweep
-    const bool do_shift = (NCOL != 1) && a.shift_on && !(a.dbg_skip & 2);
+    const bool do_shift = (NCOL != 1) && a.shift_on && !PMC_DBG_BIT(a, 2);
     const int sdir = (a.shift_d <= 0.0f) ? -1 : 1;                       // shiftCells.h:38-44
     const int sdx = (do_shift && a.shift_f == 0) ? sdir : 0, sdy = (do_shift && a.shift_f == 1) ? sdir : 0;
     // staged area = region + one upstream row / column; (xoff, yoff) = staged coords of region (0, 0)
@@ -361,7 +351,7 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
 
 #pragma unroll 1
-    for (int k = 0; k < ((a.dbg_skip & 1) ? 0 : NCOL); k++) {
+    for (int k = 0; k < (PMC_DBG_BIT(a, 1) ? 0 : NCOL); k++) {
         const int lo = (NCOL == 1) ? H : k + 1;     // cells closer than lo to the region edge are stale
         const int pi = ((int)((a.offmask >> (2 * k)) & 1u) - rx0) & 1;       // region-column parity of the active colour
         const int pj = ((int)((a.offmask >> (2 * k + 1)) & 1u) - (g.row0 + ry0)) & 1;
@@ -453,8 +443,8 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
                     const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
                     const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-                    const float px = __fmaf_rn(signed_odd23(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
-                    const float py = __fmaf_rn(signed_odd23(rw[2 * s + 1]), dscale, y);
+                    const float px = __fmaf_rn(grid_disp(rw[2 * s], g.nM2, g.mofs), dscale, x);     // make_move subsweep.h:60-71
+                    const float py = __fmaf_rn(grid_disp(rw[2 * s + 1], g.nM2, g.mofs), dscale, y);
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
@@ -516,8 +506,8 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     float *fx = slot_ptr(it), *fy = fx + 2 * PL * 4;
                     it = (it + 1 >= cnt) ? 0 : it + 1;
                     const float x = *fx, y = *fy;
-                    const float px = __fmaf_rn(signed_odd23(ra), dscale, x);
-                    const float py = __fmaf_rn(signed_odd23(rb), dscale, y);
+                    const float px = __fmaf_rn(grid_disp(ra, g.nM2, g.mofs), dscale, x);
+                    const float py = __fmaf_rn(grid_disp(rb, g.nM2, g.mofs), dscale, y);
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     if (m >= 0.0f) {
@@ -534,7 +524,7 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
     }
 
     // ------------------------------------------------------------ phase 5: owned tile -> HBM
-    if (!(a.dbg_skip & 4)) {
+    if (!PMC_DBG_BIT(a, 4)) {
         constexpr int CSTEP = THREADS / 4, DJ = CSTEP / TX, DI = CSTEP % TX;
         const int plane = tid & 3;
         int c = tid >> 2;
@@ -623,9 +613,6 @@ cudaError_t pmc_launch_fused_sweep(const DevGeom &g, const float4 *din, const in
                                    float4 *dout, int16_t *nout, const SweepArgs &a,
                                    Counters *ctr, cudaStream_t st)
 {
-    // tuning knob (PMC_TILE): 0 = 26x32 tile, 2 CTAs/SM; 1 = 26x20, 3 CTAs/SM; 2 = 26x38, 2 CTAs/SM
-    static const int tile = [] { const char *e = getenv("PMC_TILE"); return e ? atoi(e) : 0; }();
-    if (tile == 1) return launch_fused_cfg<26, 20, 224, 3>(g, din, nin, dout, nout, a, ctr, st);
-    if (tile == 2) return launch_fused_cfg<26, 38, 352, 2>(g, din, nin, dout, nout, a, ctr, st);
+    // 26 x 32 tile, 2 CTAs/SM (the 26 x 20 / 3 CTAs and 26 x 38 / 2 CTAs variants measured slower; round 1)
     return launch_fused_cfg<kTX4, kTY4, kThreads4, kMinB4>(g, din, nin, dout, nout, a, ctr, st);
 }

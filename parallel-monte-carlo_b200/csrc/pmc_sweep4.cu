@@ -37,6 +37,7 @@
 #include "pmc_internal.cuh"
 #include <cuda.h>      // CUtensorMap type only; the encoder comes from cudaGetDriverEntryPoint
 #include <stdlib.h>
+#include <atomic>
 
 namespace {
 
@@ -158,16 +159,6 @@ __device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float np
         }
     }
     return m;
-}
-
-// odd integer 2k + 1, k = (top 23 bits of r) - 2^22: symmetric, exact in binary32, without I2F
-__device__ __forceinline__ float signed_odd23(uint32_t r)
-{
-    // 2^23 + (r >> 9) as a float straight from the integer multiplier (no shift / mask on the ALU pipe)
-    uint32_t tb;
-    asm("mad.hi.u32 %0, %1, 8388608, 1258291200;" : "=r"(tb) : "r"(r));     // (r * 2^23 >> 32) + 0x4B000000
-    const float k = __fadd_rn(__uint_as_float(tb), -12582912.0f);             // (r >> 9) - 2^22, exact
-    return __fmaf_rn(k, 2.0f, 1.0f);
 }
 
 // V2 shiftCells.h:23-112 for one destination cell.  The result is scattered in place into the
@@ -357,8 +348,8 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
         const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
         const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-        const float px = __fmaf_rn(signed_odd23(rw[2 * s]), dscale, x);     // make_move subsweep.h:60-71
-        const float py = __fmaf_rn(signed_odd23(rw[2 * s + 1]), dscale, y);
+        const float px = __fmaf_rn(grid_disp(rw[2 * s], g.nM2, g.mofs), dscale, x);     // make_move subsweep.h:60-71
+        const float py = __fmaf_rn(grid_disp(rw[2 * s + 1], g.nM2, g.mofs), dscale, y);
         bool inb;
         float m = neighbours_min_d2(px, py, inb);
         // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
@@ -593,7 +584,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     const int HX = a.hx, HY = a.hy;                 // halo this sweep's colour order needs, per axis (2..4)
 
     // this sweep's grid shift: the tile carries one extra row / column on the upstream side
-    const bool do_shift = a.shift_on && !(a.dbg_skip & 2);
+    const bool do_shift = a.shift_on && !PMC_DBG_BIT(a, 2);
     const int sdir = (a.shift_d <= 0.0f) ? -1 : 1;                       // shiftCells.h:38-44
     const int exl = (do_shift && a.shift_f == 0 && sdir < 0), exh = (do_shift && a.shift_f == 0 && sdir > 0);
     const int eyl = (do_shift && a.shift_f == 1 && sdir < 0), eyh = (do_shift && a.shift_f == 1 && sdir > 0);
@@ -633,7 +624,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
         const int bx0 = t.X0 >> kFB, nbx = ((t.X0 + t.RX - 1) >> kFB) - bx0 + 1;
         const int by0 = t.Y0 >> kFB, nby = ((t.Y0 + t.RY - 1) >> kFB) - by0 + 1;
         static_assert(((TL::PITCH - 1) >> kFB) + 2 <= 32, "flag lanes");
-        if ((tid & 31) < nbx && !(a.dbg_skip & 32))
+        if ((tid & 31) < nbx && !PMC_DBG_BIT(a, 32))
             for (int by = tid >> 5; by < nby; by += kNT / 32)
                 crowded |= __ldg(a.flag_in + (by0 + by) * g.FW + bx0 + (tid & 31)) == a.epoch_in;
         if (a.dbg_skip & 8) crowded = 1;
@@ -673,7 +664,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
 
     // ------------------------------------------------------------ the four sub-sweeps
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
-    if (!(a.dbg_skip & 1)) {
+    if (!PMC_DBG_BIT(a, 1)) {
         if (ns4) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
@@ -709,7 +700,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     }
 
     // ------------------------------------------------------------ owned tile -> HBM
-    if (!(a.dbg_skip & 4)) store_pass<TL, NPL>(sm, t, g, a, dout, do_shift, col0, row0, tid);
+    if (!PMC_DBG_BIT(a, 4)) store_pass<TL, NPL>(sm, t, g, a, dout, do_shift, col0, row0, tid);
     return false;
 }
 
@@ -881,15 +872,15 @@ cudaError_t launch_cfg(const Geom4 &g, const void *tmap_in, const void *tmap_hal
 {
     constexpr int SMEM = (int)((FAST ? 3 : 4) * BoxF::PLANE_BYTES);
     auto kern = sweep4_kernel<MINB, FAST>;
-    static bool attr_set[64] = { false };           // function attributes are per device
+    static std::atomic<unsigned long long> attr_set{ 0ull };   // function attributes are per device; setting twice is harmless
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (dev < 0 || dev >= 64 || !((attr_set.load(std::memory_order_acquire) >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set.fetch_or(1ull << dev, std::memory_order_release);
     }
     if (a_in.tx < 2 || a_in.ty < 2) return cudaErrorInvalidValue;      // pmc4_plan_sweep was not called
     const int gy = (g.rows + a_in.ty - 1) / a_in.ty;

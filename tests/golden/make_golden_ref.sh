@@ -13,3 +13,9 @@ out=${1:-gpurun_out/ref}
 mkdir -p "$out"
 for s in 1 2 3; do ./oracle/_ref/ref_harness $s 40 > "$out/ref_kernels_seed$s.json"; done
 ./oracle/_ref/ref_harness 7 24 > "$out/ref_kernels_seed7.json"
+for s in 4 5 6 8 9 10; do ./oracle/_ref/ref_harness $s 40 > "$out/ref_kernels_seed$s.json"; done
+# crowded cells (7-8 particles, immigrant overflow beyond our nmax = 8)
+for s in 11 12 13 14; do ./oracle/_ref/ref_harness $s 44 14 > "$out/ref_kernels_seed$s.json"; done
+for s in 15 16; do ./oracle/_ref/ref_harness $s 52 18 > "$out/ref_kernels_seed$s.json"; done
+# the sub-sweep device functions of subsweep.h on the probes of tests/golden/make_trial_probes.py
+./oracle/_ref/ref_harness_v1 < tests/golden/trial_probes_in.txt > "$out/ref_trials.json"
