@@ -94,6 +94,7 @@ def lib():
     L.pmc_set_stream.argtypes = [hp, vp]
     L.pmc_set_blocking.argtypes = [hp, C.c_int]
     L.pmc_synchronize.argtypes = [hp]
+    L.pmc_set_tuning.argtypes = [hp, C.c_char_p, C.c_int]
     L.pmc_error_string.argtypes = [C.c_int]
     L.pmc_error_string.restype = C.c_char_p
     L.pmc_init_r.argtypes = [hp, vp]
@@ -115,6 +116,7 @@ def lib():
     L.pmc_pressure_from_hist.argtypes = [hp, vp, C.c_float, C.c_int, C.c_int64, vp,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pmc_disk_to_r_host.argtypes = [hp, vp, vp, vp, C.POINTER(C.c_int64)]
+    L.pmc_disk_to_r.argtypes = [hp, vp, vp, vp, C.POINTER(C.c_int64)]
     L.pmc_run_host.argtypes = [hp, vp, C.c_uint64, C.c_int, vp, vp]
     L.pmc_geometry_from_params.argtypes = [C.POINTER(Params), C.POINTER(Geometry)]
     L.pmc_rsa_host.argtypes = [C.POINTER(Params), C.c_uint64, vp, C.POINTER(C.c_int64)]
@@ -129,11 +131,11 @@ def lib():
 
 
 EXPORTS = ["pmc_create", "pmc_destroy", "pmc_get_geometry", "pmc_r_bytes", "pmc_disk_bytes",
-           "pmc_n_bytes", "pmc_set_stream", "pmc_set_blocking", "pmc_synchronize",
+           "pmc_n_bytes", "pmc_set_stream", "pmc_set_blocking", "pmc_synchronize", "pmc_set_tuning",
            "pmc_error_string", "pmc_init_r", "pmc_assign", "pmc_subsweep", "pmc_shift_cells",
            "pmc_schedule", "pmc_colour_to_off", "pmc_plan_sweep", "pmc_sweep", "pmc_get_counters",
            "pmc_reset_counters", "pmc_get_kernel_time", "pmc_get_launch_count", "pmc_check", "pmc_gr_hist", "pmc_pressure_from_hist",
-           "pmc_disk_to_r_host", "pmc_run_host", "pmc_geometry_from_params", "pmc_rsa_host",
+           "pmc_disk_to_r_host", "pmc_disk_to_r", "pmc_run_host", "pmc_geometry_from_params", "pmc_rsa_host",
            "pmc_write_dump", "pmc_save_checkpoint", "pmc_load_checkpoint", "pmc_comm_unique_id", "pmc_comm_init",
            "pmc_exchange_ghosts"]
 
@@ -176,7 +178,20 @@ def _ck(rc):
 
 
 class ParallelMC:
-    """One simulation handle on one GPU (or one slab of a multi-GPU run)."""
+    """One simulation handle on one GPU (or one slab of a multi-GPU run).
+
+    strict (default True): a blocking call during which a cell overflowed nmax or particles fell outside the
+    box raises PmcError (PMC_E_OVERFLOW / PMC_E_LOST).  With strict = False the code is kept in
+    `last_warning` instead (the reference itself writes past nmax silently and carries on); the totals are in
+    counters() either way."""
+    strict = True
+    last_warning = 0
+
+    def _ckw(self, rc):
+        if rc in (-3, -4) and not self.strict:
+            self.last_warning = rc
+            return
+        _ck(rc)
 
     def __init__(self, n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4,
                  move_delta=0.1, seed=1234, cps_multiple=2, device=-1, rank=0, n_ranks=1):
@@ -215,6 +230,10 @@ class ParallelMC:
     def synchronize(self):
         _ck(lib().pmc_synchronize(self._h))
 
+    def set_tuning(self, name, value):
+        """Result-invariant knobs (pmc_set_tuning): bands, prefetch, overlap, generic, force_crowded, no_ns4, full_halo."""
+        _ck(lib().pmc_set_tuning(self._h, name.encode(), int(value)))
+
     def alloc_r(self):
         return self.torch.empty((2, self.geom.n_particles), dtype=self.torch.float32, device=self.device)
 
@@ -233,15 +252,15 @@ class ParallelMC:
     def assign(self, r, disk=None, n=None):
         if disk is None:
             disk, n = self.alloc_cells()
-        _ck(lib().pmc_assign(self._h, r.data_ptr(), disk.data_ptr(), n.data_ptr()))
+        self._ckw(lib().pmc_assign(self._h, r.data_ptr(), disk.data_ptr(), n.data_ptr()))
         return disk, n
 
     def subsweep(self, disk, n, off, sweep):
         o = (C.c_int * 2)(*off)
-        _ck(lib().pmc_subsweep(self._h, disk.data_ptr(), n.data_ptr(), o, sweep))
+        self._ckw(lib().pmc_subsweep(self._h, disk.data_ptr(), n.data_ptr(), o, sweep))
 
     def shift_cells(self, disk, n, f, d):
-        _ck(lib().pmc_shift_cells(self._h, disk.data_ptr(), n.data_ptr(), f, C.c_float(d)))
+        self._ckw(lib().pmc_shift_cells(self._h, disk.data_ptr(), n.data_ptr(), f, C.c_float(d)))
 
     def schedule(self, sweep):
         order = (C.c_int * 4)()
@@ -257,7 +276,7 @@ class ParallelMC:
         return [o[0], o[1]]
 
     def sweep(self, disk, n, sweep0, n_sweeps):
-        _ck(lib().pmc_sweep(self._h, disk.data_ptr(), n.data_ptr(), sweep0, n_sweeps))
+        self._ckw(lib().pmc_sweep(self._h, disk.data_ptr(), n.data_ptr(), sweep0, n_sweeps))
 
     # counters / observables ---------------------------------------------------
     def counters(self):
@@ -311,9 +330,16 @@ class ParallelMC:
         _ck(lib().pmc_disk_to_r_host(self._h, disk.data_ptr(), n.data_ptr(), r.ctypes.data, C.byref(k)))
         return r, k.value
 
+    def disk_to_r(self, disk, n, r=None):
+        """disk_to_r (kernel.cu:497-507) on the device: (r [2][N] global coordinates, particles found)."""
+        r = self.alloc_r() if r is None else r
+        k = C.c_int64()
+        _ck(lib().pmc_disk_to_r(self._h, disk.data_ptr(), n.data_ptr(), r.data_ptr(), C.byref(k)))
+        return r, k.value
+
     def run_host(self, r_host, sweep0, n_sweeps, disk_host, n_host):
         """End to end with host buffers (torch CPU tensors, ideally pinned)."""
-        _ck(lib().pmc_run_host(self._h, r_host.data_ptr(), sweep0, n_sweeps,
+        self._ckw(lib().pmc_run_host(self._h, r_host.data_ptr(), sweep0, n_sweeps,
                                disk_host.data_ptr(), n_host.data_ptr()))
 
     # initial configurations / trajectory / checkpoint ---------------------------

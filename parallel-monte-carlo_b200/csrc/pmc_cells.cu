@@ -46,7 +46,7 @@ __device__ __forceinline__ float to_local(float x, int c, const DevGeom &g)
 {
     const double origin = __dsub_rn(__dmul_rn((double)c, (double)g.w), __dmul_rn(g.L_box, 0.5));
     const double q = (double)g.dscale;
-    double k = rint(__ddiv_rn(__dsub_rn((double)x, origin), q));    // exact scaling by a power of two, ties to even
+    double k = rint(__dmul_rn(__dsub_rn((double)x, origin), 1.0 / q));    // q = 2^e: exact scaling (no division), ties to even
     k = fmin(k, (double)g.K);
     k = fmax(k, 1.0);
     return (float)__dmul_rn(k, q);

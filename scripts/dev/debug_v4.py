@@ -1,7 +1,7 @@
-"""Development aid: isolate the phases of the v4 fused sweep with PMC_DBG_SKIP
+"""Development aid (needs a library built with -DPMC_DEBUG): isolate the phases of the v4 fused sweep with PMC_DBG_SKIP
 (1 = no sub-sweeps, 2 = no shift, 4 = no store; 8, 32, 64: see pmc_internal.cuh) and compare against the oracle."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import pmc_b200
 from oracle import oracle as O

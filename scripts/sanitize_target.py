@@ -18,6 +18,7 @@ torch.cuda.synchronize()
 import numpy as np
 sigma, lam, N = 0.25, 1.5, 2 ** 14
 mc2 = pmc_b200.ParallelMC(N, sigma_d=sigma, phi=float(lam * np.pi * sigma * sigma / 16.0), cell_w=2.0, move_delta=0.3, n_M=4)
+mc2.strict = False          # overflow may happen here: counted, not raised
 rng = np.random.default_rng(12)
 hl = np.float32(mc2.geom.L / 2)
 r = (rng.random((2, N), dtype=np.float32) * 2 - 1) * hl * np.float32(0.9999)

@@ -57,7 +57,14 @@ def test_assign_random_points_slot_order_and_lost():
     rng = np.random.default_rng(3)
     r = ((rng.random((2, 2 ** 14)) - 0.5) * o.g.L * 1.002).astype(np.float32)   # a few outside the box
     odisk, on = o.assign(r)
+    import pmc_b200
+    with pytest.raises(pmc_b200.PmcError) as ei:      # blocking call + dropped particles = a return code, not silence
+        mc.assign(torch.from_numpy(r).cuda())
+    assert ei.value.code in (-3, -4)
+    mc.strict = False                                 # the reference's own behaviour: carry on, counters tell
+    mc.reset_counters()
     disk, n = mc.assign(torch.from_numpy(r).cuda())
+    assert mc.last_warning in (-3, -4)
     c = mc.counters()
     assert o.lost > 0 and c["lost"] == o.lost and (c["status"] & 2)
     if not (c["status"] & 1):            # no overflow: slot order must be the reference's
@@ -236,10 +243,19 @@ def test_overflow_is_reported_not_silent():
     mc, o = pair(4096, sigma_d=0.01, phi=0.70 * 1e-4)
     r = o.init_r()
     r[:, :12] = r[:, :1] + (np.arange(12, dtype=np.float32) * 1e-3)[None, :]
+    import pmc_b200
+    with pytest.raises(pmc_b200.PmcError) as ei:
+        mc.assign(torch.from_numpy(r).cuda())
+    assert ei.value.code == -3                        # PMC_E_OVERFLOW
+    mc.strict = False
     disk, n = mc.assign(torch.from_numpy(r).cuda())
     c = mc.counters()
     assert c["status"] & 1 and c["lost"] >= 1
     assert int(n.max()) <= 8
+    # geometries whose mean occupancy leaves no head-room are refused up front (cell_w = 3 sigma at phi = 0.7: mean 8)
+    with pytest.raises(pmc_b200.PmcError) as ei:
+        pmc_b200.ParallelMC(4096, **dict(KW, cell_w=3.0))
+    assert ei.value.code == -2
 
 
 # ---------------------------------------------------------------- end to end with host buffers
@@ -260,6 +276,19 @@ def test_run_host_round_trip():
     rg, k = mc.disk_to_r_host(disk, n)
     ro, ko = o.disk_to_r(odisk, on)
     assert k == ko == 2 ** 14 and np.array_equal(bits(rg), bits(ro))
+
+
+def test_disk_to_r_on_the_device_matches_the_oracle_and_the_host_variant():
+    """pmc_disk_to_r (device scan + scatter) == oracle_disk_to_r (kernel.cu:497-507 order) == pmc_disk_to_r_host."""
+    mc, o = pair(2 ** 16)
+    disk, n = mc.assign(mc.init_r())
+    mc.sweep(disk, n, 0, 5)
+    r_dev, k = mc.disk_to_r(disk, n)
+    r_host, kh = mc.disk_to_r_host(disk, n)
+    r_or, ko = o.disk_to_r(disk.cpu().numpy(), n.cpu().numpy())
+    assert k == kh == ko == 2 ** 16
+    assert np.array_equal(bits(r_dev.cpu().numpy()), bits(r_or)) and np.array_equal(bits(r_host), bits(r_or))
+    # (no round trip through pmc_assign: float32 GLOBAL coordinates lose the low bits of the cell-local ones, SURVEY H2)
 
 
 # ---------------------------------------------------------------- the exact no-overlap invariant
@@ -332,6 +361,7 @@ def test_assign_and_shift_cells_match_the_reference_kernels_on_gpu(seed):
     mc = pmc_b200.ParallelMC(p["n_real"], phi=float(o.phi), sigma_d=1.0, cell_w=2.5, nmax=8, n_M=4,
                              move_delta=0.1, seed=1)
     assert mc.geom.cps == 4 and mc.geom.w == 2.5 and mc.geom.L == 10.0
+    mc.strict = False       # the fixtures drop particles on purpose (lower box face, cells beyond nmax)
     r = torch.tensor(np.array(gold["r"], dtype=np.float32)[:2].copy(), device="cuda")
     disk, n = mc.assign(r)
     excess = _assert_matches_reference_step(o, disk.cpu().numpy(), n.cpu().numpy(), gold["steps"][0])
@@ -439,6 +469,7 @@ def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
     sigma, lam, N = 0.25, 3.0, 2 ** 16
     phi = lam * np.pi * sigma * sigma / 16.0          # occupancy = 16 phi / (pi sigma^2) at w = 2
     mc, o = pair(N, sigma_d=sigma, phi=float(phi), cell_w=2.0, move_delta=0.3)
+    mc.strict = False                                 # overflow is part of this test: counted, not raised
     rng = np.random.default_rng(12)
     hl = np.float32(o.g.L / 2)
     r = (rng.random((2, N), dtype=np.float32) * 2 - 1) * hl * np.float32(0.9999)
@@ -454,19 +485,37 @@ def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
     assert c["lost"] > 0 and c["status"] & 1
 
 
-def test_crowded_tile_path_is_bit_exact_on_ordinary_tiles():
-    """PMC_DBG_SKIP=8 sends EVERY tile of the fused sweep down the crowded-tile path (two half-height
-    tiles with all four planes staged) instead of the 3-plane fast path; the result must not change.
-    The switch is read once per process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PMC_DBG_SKIP="8", PMC_S="7", PMC_N=str(2 ** 16))
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "debug_v4.py")], env=env,
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
-    assert "count mismatches 0" in out.stdout and "position mismatches 0" in out.stdout, out.stdout[-1500:]
+@pytest.mark.parametrize("knob", ["force_crowded", "no_ns4", "full_halo", "generic", "bands1"])
+def test_tuning_knobs_never_change_the_result(knob):
+    """pmc_set_tuning chooses which kernel / schedule computes the sweep, never the result: "force_crowded"
+    sends EVERY tile down the crowded-tile path (half-height pieces with all four planes staged), "full_halo"
+    disables the per-colour-order halo planning, "generic" uses the cp.async kernel of pmc_sweep.cu, "bands"
+    the stream schedule.  Bit-identical to the oracle (and hence to the default path) every time."""
+    N, S = 2 ** 16, 7
+    mc, o = pair(N)
+    if knob == "bands1":
+        mc.set_tuning("bands", 1)
+    else:
+        mc.set_tuning(knob, 1)
+    disk, n = mc.assign(mc.init_r())
+    odisk, on = o.assign(o.init_r())
+    mc.sweep(disk, n, 0, S)
+    o.sweep(odisk, on, 0, S)
+    assert_same_state(disk, n, odisk, on)
+    c = mc.counters()
+    assert (c["trials"], c["accepted"]) == (o.trials.value, o.accepted.value)
+    import pmc_b200
+    with pytest.raises(pmc_b200.PmcError):
+        mc.set_tuning("skip_subsweeps", 1)            # nothing that changes results is reachable
+
+
+def test_library_reads_no_result_changing_environment_variable():
+    """Round 1 read PMC_DBG_SKIP / PMC_FAST / PMC_OVERLAP / PMC_TILE / PMC_FORCE_GENERIC from the environment in
+    the product path; those strings no longer exist in the shipped library."""
+    import pmc_b200
+    blob = open(pmc_b200.LIB_PATH, "rb").read()
+    for name in (b"PMC_DBG_SKIP", b"PMC_FAST", b"PMC_OVERLAP", b"PMC_TILE", b"PMC_FORCE_GENERIC"):
+        assert name not in blob, name
 
 
 def test_cells_that_become_crowded_on_the_fast_path():
