@@ -13,6 +13,8 @@
  *   --delta <f>        sigma         start.cu:22     proposal half-width
  *   --passes <n>       MCpasses      start.cu:24     sweeps
  *   --seed <n>         1234          subsweep.h:259
+ *   --proposal <uniform|gaussian>    subsweep.h:64   trial displacement: uniform square (bit-exact, fast kernel) or the
+ *                                                     reference's curand_normal * sigma (generic kernel)
  *   --rsa                                             random-sequential-addition start instead of init_r's lattice
  *   --fused                                           one pmc_sweep call per trace interval instead of the per-call protocol
  *   --trace [k]                                       every k sweeps (default 1): "%i: %f\n" sweep and acceptance ratio since
@@ -87,6 +89,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--delta")) { NEED; p.move_delta = (float)atof(v); }
         else if (!strcmp(a, "--passes")) { NEED; MCpasses = atoi(v); }
         else if (!strcmp(a, "--seed")) { NEED; p.seed = strtoull(v, NULL, 10); }
+        else if (!strcmp(a, "--proposal")) { NEED; p.proposal = !strcmp(v, "gaussian") ? PMC_PROPOSAL_GAUSSIAN : PMC_PROPOSAL_UNIFORM; }
         else if (!strcmp(a, "--dump")) { NEED; dump = v; }
         else if (!strcmp(a, "--dump-every")) { NEED; dump_every = atoi(v) > 0 ? atoi(v) : 1; }
         else if (!strcmp(a, "--checkpoint")) { NEED; ckpt = v; }

@@ -78,7 +78,18 @@ typedef struct pmc_params {
     int      device;        /* CUDA device ordinal, -1 = current */
     int      rank;          /* slab index in [0, n_ranks) */
     int      n_ranks;       /* number of slabs (GPUs); 0 or 1 = single GPU */
+    int      proposal;      /* PMC_PROPOSAL_UNIFORM (0, default) or PMC_PROPOSAL_GAUSSIAN (1): see below */
 } pmc_params;
+
+/* Trial displacement (make_move subsweep.h:60-71; reference: x + curand_normal * sigma per axis):
+ *   PMC_PROPOSAL_UNIFORM   uniform in the square [-move_delta, move_delta]^2 on the coordinate grid: integer
+ *                          arithmetic only, CPU oracle and GPU agree BIT FOR BIT, served by the fast kernel;
+ *   PMC_PROPOSAL_GAUSSIAN  the reference's N(0, move_delta^2) per axis (Box-Muller on the Philox words, rounded
+ *                          to the grid, signs from separate bits: exactly symmetric).  Uses logf / sincospif, so
+ *                          a CPU and the GPU agree statistically only (tests: acceptance and contact value within
+ *                          3 sigma over seeds); served by the generic kernel. */
+#define PMC_PROPOSAL_UNIFORM  0
+#define PMC_PROPOSAL_GAUSSIAN 1
 
 typedef struct pmc_geometry {
     int64_t n_particles;
@@ -113,7 +124,7 @@ int  pmc_set_blocking(pmc_handle *h, int blocking);      /* default 1 (start.cu 
 int  pmc_synchronize(pmc_handle *h);
 /* Knobs that choose WHICH kernel / schedule computes the result, never the result itself (bit-identical for
  * every setting; tests use them to drive the rare paths): "bands" 1..8, "prefetch" >= 0, "overlap" 0/1,
- * "generic" 0/1, "force_crowded" 0/1, "no_ns4" 0/1, "full_halo" 0/1.  Unknown name: PMC_E_INVALID.
+ * "generic" 0/1, "four_plane" 0/1, "force_crowded" 0/1, "no_ns4" 0/1, "full_halo" 0/1.  Unknown name: PMC_E_INVALID.
  * The library reads no environment variable that can change a result. */
 int  pmc_set_tuning(pmc_handle *h, const char *name, int value);
 const char *pmc_error_string(int code);

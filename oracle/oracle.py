@@ -20,7 +20,7 @@ class Geom(C.Structure):
         ("nmax", C.c_int), ("n_M", C.c_int), ("w", C.c_float), ("L", C.c_float),
         ("half_L", C.c_float), ("sigma", C.c_float), ("sigma2", C.c_float),
         ("delta", C.c_float), ("dscale", C.c_float), ("L_box", C.c_double),
-        ("seed", C.c_uint64), ("K", C.c_int), ("M", C.c_int),
+        ("seed", C.c_uint64), ("K", C.c_int), ("M", C.c_int), ("proposal", C.c_int),
     ]
 
 
@@ -103,12 +103,13 @@ class Oracle:
     """Host-side mirror of the C-ABI handle (include/pmc.h) on top of the C oracle."""
 
     def __init__(self, n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4,
-                 move_delta=0.1, seed=1234, cps_multiple=2):
+                 move_delta=0.1, seed=1234, cps_multiple=2, proposal=0):
         self.g = Geom()
         rc = lib().oracle_make_geom(n_particles, phi, sigma_d, cell_w, nmax, n_M, move_delta,
                                     seed, cps_multiple, C.byref(self.g))
         if rc:
             raise ValueError(f"oracle_make_geom failed rc={rc}")
+        self.g.proposal = int(proposal)         # 0 uniform square (default), 1 the reference's Gaussian
         self.trials = C.c_uint64(0)
         self.accepted = C.c_uint64(0)
         self.lost = 0

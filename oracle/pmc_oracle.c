@@ -300,6 +300,19 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
          * bits of the words feed the shuffle above.)  x + m*q is exact. */
         int mx = (int)((((uint64_t)(ra >> 8) * 2u + 1u) * nM2) >> 25) - g->M;
         int my = (int)((((uint64_t)(rb >> 8) * 2u + 1u) * nM2) >> 25) - g->M;
+        if (g->proposal == 1) {
+            /* the reference's proposal, make_move subsweep.h:60-71: x + curand_normal * sigma per axis.
+             * Box-Muller on bits 8..30 of the two words (radius from ra, angle in the first quadrant from
+             * rb), the signs from bit 31 of each word: P(m) == P(-m) exactly whatever libm does. */
+            float u1 = ((float)((ra >> 8) & 0x7FFFFFu) + 0.5f) * 1.1920928955078125e-07f;   /* (0, 1) */
+            float u2 = ((float)((rb >> 8) & 0x7FFFFFu) + 0.5f) * 5.9604644775390625e-08f;   /* (0, 1/2) */
+            float rr = sqrtf(-2.0f * logf(u1)) * (float)g->M;
+            float ang = 3.14159265358979323846f * u2;
+            mx = (int)rintf(rr * cosf(ang));
+            my = (int)rintf(rr * sinf(ang));
+            if (ra >> 31) mx = -mx;
+            if (rb >> 31) my = -my;
+        }
         float px = fmaf((float)mx, g->dscale, X[slot]);
         float py = fmaf((float)my, g->dscale, Y[slot]);
         (*trials)++;

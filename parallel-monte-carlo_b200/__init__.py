@@ -38,7 +38,7 @@ class Params(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("phi", C.c_float), ("sigma_d", C.c_float),
                 ("cell_w", C.c_float), ("nmax", C.c_int), ("n_M", C.c_int),
                 ("move_delta", C.c_float), ("seed", C.c_uint64), ("cps_multiple", C.c_int),
-                ("device", C.c_int), ("rank", C.c_int), ("n_ranks", C.c_int)]
+                ("device", C.c_int), ("rank", C.c_int), ("n_ranks", C.c_int), ("proposal", C.c_int)]
 
 
 class Geometry(C.Structure):
@@ -155,7 +155,7 @@ def plan_sweep(order, f, d):
 def geometry_from_params(n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4, move_delta=0.1,
                          seed=1234, cps_multiple=2, rank=0, n_ranks=1):
     """Geometry derivation without a device (pure host maths in the C library)."""
-    p = Params(n_particles, phi, sigma_d, cell_w, nmax, n_M, move_delta, seed, cps_multiple, -1, rank, n_ranks)
+    p = Params(n_particles, phi, sigma_d, cell_w, nmax, n_M, move_delta, seed, cps_multiple, -1, rank, n_ranks, 0)
     g = Geometry()
     _ck(lib().pmc_geometry_from_params(C.byref(p), C.byref(g)))
     return g
@@ -165,7 +165,7 @@ def rsa_host(n_particles, seed=1, **kw):
     """Random sequential addition on the host (no device needed): numpy r [2][N], attempts."""
     import numpy as np
     p = Params(n_particles, kw.get("phi", 0.30), kw.get("sigma_d", 1.0), kw.get("cell_w", 2.0), 8, 4,
-               kw.get("move_delta", 0.1), 1234, kw.get("cps_multiple", 2), -1, 0, 1)
+               kw.get("move_delta", 0.1), 1234, kw.get("cps_multiple", 2), -1, 0, 1, 0)
     r = np.zeros((2, n_particles), dtype=np.float32)
     att = C.c_int64()
     _ck(lib().pmc_rsa_host(C.byref(p), seed, r.ctypes.data, C.byref(att)))
@@ -194,13 +194,13 @@ class ParallelMC:
         _ck(rc)
 
     def __init__(self, n_particles, phi=0.70, sigma_d=1.0, cell_w=2.0, nmax=8, n_M=4,
-                 move_delta=0.1, seed=1234, cps_multiple=2, device=-1, rank=0, n_ranks=1):
+                 move_delta=0.1, seed=1234, cps_multiple=2, device=-1, rank=0, n_ranks=1, proposal=0):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("parallel-monte-carlo_b200 needs a CUDA device (no CPU fallback)")
         self.torch = torch
         self.params = Params(n_particles, phi, sigma_d, cell_w, nmax, n_M, move_delta, seed,
-                             cps_multiple, device, rank, n_ranks)
+                             cps_multiple, device, rank, n_ranks, proposal)
         self._h = C.c_void_p()
         _ck(lib().pmc_create(C.byref(self.params), C.byref(self._h)))
         self.geom = Geometry()

@@ -59,6 +59,7 @@ static bool nccl_load()
 // ------------------------------------------------------------------ handle
 constexpr int kMaxBands = 8;
 constexpr int kGhostRows = 5;   // fused sweep halo (4) + 1 upstream row of the pending shift
+constexpr int kFlagRows = 3;    // rows of 2 x 2 flag blocks that cover kMY = 5 rows starting at an odd or even row
 
 struct pmc_handle {
     pmc_params p;
@@ -98,10 +99,11 @@ struct pmc_handle {
     cudaEvent_t ev_band[2][kMaxBands], ev_band_start;
     // crowded-cell flags of the two internal buffers (one word per 2 x 2 cells, epoch-stamped)
     unsigned *v4_flags[2];
+    unsigned *v4_flag_stage;    // slab ring: the neighbours' flag rows land here and are merged
     unsigned v4_epoch[2], v4_epoch_next;
     long long launches;         // kernels launched by this handle since the last pmc_reset_counters
     // result-invariant tuning knobs (pmc_set_tuning)
-    int tune_bands, tune_prefetch, tune_overlap, tune_generic, tune_force;
+    int tune_bands, tune_prefetch, tune_overlap, tune_generic, tune_force, tune_four_plane;
     unsigned status_sticky;     // status bits already handed to the caller as a return code (pmc_get_counters ORs them back in)
     Counters *h_ctr;            // pinned host mirror for the status read of blocking calls
     alignas(64) unsigned char v4_tmap[2][2][128];   // [buffer][0: full-tile box, 1: half-height box]
@@ -152,6 +154,7 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     if (p.n_particles <= 0 || !(p.phi > 0.0f) || !(p.sigma_d > 0.0f) || !(p.cell_w >= p.sigma_d) ||
         p.n_M < 1 || p.n_M > 64 || !(p.move_delta > 0.0f)) return PMC_E_INVALID;
     if (p.nmax != PMC_NMAX) return PMC_E_UNSUPPORTED;
+    if (p.proposal != PMC_PROPOSAL_UNIFORM && p.proposal != PMC_PROPOSAL_GAUSSIAN) return PMC_E_INVALID;
     // a cell of width w holds pi/4 * w^2 * phi / (pi sigma^2 / 4) disks on average; with less than two slots
     // of head-room above that mean, overflow is the rule rather than a 1e-5 event (cell_w = 3 sigma at
     // phi = 0.7: mean 8.0).  Overflow at run time is still detected and reported (PMC_E_OVERFLOW).
@@ -182,6 +185,7 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     g.sigma = p.sigma_d;
     g.sigma2 = p.sigma_d * p.sigma_d;
     g.dscale = (float)q;
+    g.proposal = p.proposal;
     g.n_M = p.n_M;
     g.seed_lo = (unsigned)p.seed;
     g.seed_hi = (unsigned)(p.seed >> 32);
@@ -257,7 +261,8 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
         q.seed_lo = g.seed_lo; q.seed_hi = g.seed_hi;
         q.try_ns4 = (double)p.n_particles / ((double)g.cps * (double)g.cps) < 2.5;   // a performance hint only
         for (int r = 0; r < 10; r++) { q.pk0[r] = g.seed_lo + (unsigned)r * 0x9E3779B9u; q.pk1[r] = g.seed_hi + (unsigned)r * 0xBB67AE85u; }
-        h->v4_ok = (p.n_M == 4) && ((double)g.w >= 2.0 * (double)p.sigma_d * (1.0 + 1e-5)) && g.cps >= 48 &&
+        h->v4_ok = (p.n_M == 4) && (p.proposal == PMC_PROPOSAL_UNIFORM) &&
+                   ((double)g.w >= 2.0 * (double)p.sigma_d * (1.0 + 1e-5)) && g.cps >= 48 &&
                    g.rows >= 2 * kMY && (p.n_ranks == 1 || kGhostRows == kMY);
     }
     // tuning defaults; PMC_BANDS / PMC_PREFETCH remain as documented environment overrides of the two
@@ -303,7 +308,7 @@ int pmc_destroy(pmc_handle *h)
     cudaFree(h->d_out4); cudaFree(h->d_min); cudaFree(h->d_hist);
     cudaFree(h->run_r); cudaFree(h->run_disk); cudaFree(h->run_n);
     cudaFree(h->v4_buf[0]); cudaFree(h->v4_buf[1]);
-    cudaFree(h->v4_flags[0]); cudaFree(h->v4_flags[1]);
+    cudaFree(h->v4_flags[0]); cudaFree(h->v4_flags[1]); cudaFree(h->v4_flag_stage);
     if (h->ktime_pending) {
         for (auto &pr : *h->ktime_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         delete h->ktime_pending;
@@ -328,6 +333,7 @@ int pmc_destroy(pmc_handle *h)
 //   "prefetch" (>= 0)     L2 prefetch distance in CTAs (default 296)
 //   "overlap" (0/1)       slab runs: boundary rows + NCCL ring on a side stream (default 1)
 //   "generic" (0/1)       use the generic fused kernel (pmc_sweep.cu) even where the fast path qualifies
+//   "four_plane" (0/1)    fast path with all four planes staged and no crowded-cell flag lookup (3 CTAs / SM)
 //   "force_crowded", "no_ns4", "full_halo" (0/1)   drive the rare paths of the fast kernel on ordinary tiles
 int pmc_set_tuning(pmc_handle *h, const char *name, int value)
 {
@@ -337,6 +343,7 @@ int pmc_set_tuning(pmc_handle *h, const char *name, int value)
     if (!strcmp(name, "prefetch")) { if (value < 0) return PMC_E_INVALID; h->tune_prefetch = value; return 0; }
     if (!strcmp(name, "overlap")) { h->tune_overlap = value ? 1 : 0; return 0; }
     if (!strcmp(name, "generic")) { h->tune_generic = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "four_plane")) { h->tune_four_plane = value ? 1 : 0; return 0; }
     if (!strcmp(name, "force_crowded")) return flag(8);
     if (!strcmp(name, "no_ns4")) return flag(16);
     if (!strcmp(name, "full_halo")) return flag(64);
@@ -512,23 +519,42 @@ int pmc_shift_cells(pmc_handle *h, float *d_disk, int16_t *d_n, int f, float d)
 extern "C" int pmc_get_kernel_time(pmc_handle *h, double *ms, long long *launches);
 static size_t v4_bytes(const pmc_handle *h) { return (size_t)2 * h->g4.CH * h->g4.ROWS * 4 * sizeof(float4); }
 
-// slab ring on the internal layout: whole rows (4 planes x 2 parities x CH chunks) are contiguous
-static int v4_exchange_async(pmc_handle *h, float4 *buf, cudaStream_t st)
+// slab ring on the internal layout: whole rows (4 planes x 2 parities x CH chunks) are contiguous, one message
+// per neighbour.  The crowded-cell flags of the same rows travel with them (3 rows of flag words per face, a
+// few KB), so that the tile rows next to a slab face can take the 3-plane fast kernel like every other row:
+// epochs advance identically on every rank, so a received stamp means the same thing here.  Flag blocks are
+// 2 x 2 cells and kMY is odd: the block row at a face holds one ghost and one owned row, hence the received
+// words are MERGED (a stamp is only ever added) by a tiny kernel instead of being received in place.
+static int v4_exchange_async(pmc_handle *h, float4 *buf, unsigned *flags, unsigned epoch, cudaStream_t st)
 {
     if (h->p.n_ranks <= 1) return 0;
     if (!h->comm) return PMC_E_COMM;
-    const int R = h->p.n_ranks, rows = h->g4.rows;
+    const int R = h->p.n_ranks, rows = h->g4.rows, FW = h->g4.FW;
     const int lower = (h->p.rank + R - 1) % R, upper = (h->p.rank + 1) % R;
     const size_t rp = (size_t)h->g4.CH * 128, blk = (size_t)kMY * rp;
+    const size_t fblk = (size_t)kFlagRows * FW * sizeof(unsigned);
+    if (!h->v4_flag_stage) CK(cudaMalloc(&h->v4_flag_stage, 2 * fblk));
     char *B = (char *)buf;
+    // flag rows of my lowest / highest kMY owned rows (Y = kMY .. 2 kMY - 1 and rows .. rows + kMY - 1)
+    const unsigned *f_lo = flags + (size_t)(kMY >> 1) * FW, *f_hi = flags + (size_t)(rows >> 1) * FW;
+    unsigned *r_lo = h->v4_flag_stage, *r_hi = h->v4_flag_stage + (size_t)kFlagRows * FW;
     int rc = 0;
     rc |= g_nccl.GroupStart();
     rc |= g_nccl.Send(B + (size_t)kMY * rp, blk, ncclInt8, lower, h->comm, st);
     rc |= g_nccl.Send(B + (size_t)rows * rp, blk, ncclInt8, upper, h->comm, st);
     rc |= g_nccl.Recv(B + (size_t)(kMY + rows) * rp, blk, ncclInt8, upper, h->comm, st);
     rc |= g_nccl.Recv(B, blk, ncclInt8, lower, h->comm, st);
+    rc |= g_nccl.Send(f_lo, fblk, ncclInt8, lower, h->comm, st);
+    rc |= g_nccl.Send(f_hi, fblk, ncclInt8, upper, h->comm, st);
+    rc |= g_nccl.Recv(r_hi, fblk, ncclInt8, upper, h->comm, st);
+    rc |= g_nccl.Recv(r_lo, fblk, ncclInt8, lower, h->comm, st);
     rc |= g_nccl.GroupEnd();
-    return rc ? PMC_E_COMM : 0;
+    if (rc) return PMC_E_COMM;
+    // what the lower neighbour sent are its top rows = my ghost rows Y = 0 .. kMY - 1 (flag rows 0 ..);
+    // what the upper neighbour sent are its bottom rows = my ghost rows Y = kMY + rows .. (flag rows (kMY + rows) >> 1 ..)
+    CK(pmc4_launch_flag_merge(flags, r_lo, 0, r_hi, (kMY + rows) >> 1, kFlagRows, FW, epoch, st));
+    h->launches += 1;
+    return 0;
 }
 
 // start.cu:237-260 on the fast path: caller layout -> internal layout, n_sweeps x ONE kernel
@@ -572,7 +598,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
 #endif
     const int dbg = (h->tune_force & kTuneForceBits) | dbg_env;
     const int overlap = h->tune_overlap;
-    const int fast_ok = 1;
+    const int fast_ok = !h->tune_four_plane;
     if (h->p.n_ranks > 1 && !h->comm_stream) {
         int prio_lo = 0, prio_hi = 0;               // the exchange must not queue behind the interior tiles
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -648,8 +674,8 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         const int top0 = (h->g4.rows - kMY) / a.ty;
         if (h->p.n_ranks > 1 && overlap && top0 > 1 && top0 < gy) {
             // Two streams per sweep.  Side stream (high priority): the boundary tile rows (their boxes hold
-            // ghost rows, which carry no crowded-cell flags: the 4-plane kernel), then the NCCL ring with
-            // their 5 owned rows.  Main stream: the interior rows (the fast kernel), concurrently.  Sweep t's
+            // ghost rows, whose crowded-cell flags arrive with the ring), then the NCCL ring with
+            // their 5 owned rows and flag rows.  Main stream: the interior rows (the fast kernel), concurrently.  Sweep t's
             // boundary kernel needs the interior of sweep t-1 (it reads its rows as halo and overwrites the
             // buffer it read); sweep t's interior needs the boundary rows of sweep t-1 likewise.
             const int par = t & 1;
@@ -671,8 +697,8 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
                 CK(cudaStreamWaitEvent(h->comm_stream, h->ev_band[par ^ 1][0], 0));
                 CK(cudaStreamWaitEvent(h->comm_stream, h->ev_band[par ^ 1][sbands - 1], 0));
             }
-            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->comm_stream, 0, 0, 1, top0, gy - top0)); h->launches += 1;
-            int rc = v4_exchange_async(h, dst, h->comm_stream);
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->comm_stream, fast_ok, 0, 1, top0, gy - top0)); h->launches += 1;
+            int rc = v4_exchange_async(h, dst, h->v4_flags[cur ^ 1], h->v4_epoch[cur ^ 1], h->comm_stream);
             if (rc) return rc;
             CK(cudaEventRecord(h->ev_exchanged[par], h->comm_stream));
             if (!sb) {
@@ -719,8 +745,8 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
                 CK(cudaStreamWaitEvent(h->stream, h->ev_exchanged[last_split_par], 0));
                 slab_split = 0;
             }
-            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, h->p.n_ranks == 1 ? fast_ok : 0)); h->launches += 1;
-            int rc = v4_exchange_async(h, dst, h->stream);
+            CK(pmc4_launch_sweep(h->g4, tm, tmh, dst, a, h->d_ctr, h->stream, fast_ok)); h->launches += 1;
+            int rc = v4_exchange_async(h, dst, h->v4_flags[cur ^ 1], h->v4_epoch[cur ^ 1], h->stream);
             if (rc) return rc;
         }
         cur ^= 1;
@@ -1076,7 +1102,7 @@ int pmc_write_dump(pmc_handle *h, const float *d_disk, const int16_t *d_n, const
 // (SURVEY section 5); needed for long equation-of-state runs.  The header is written field by field as
 // little-endian fixed-width integers / IEEE bit patterns (no struct padding, no compiler dependence).
 namespace {
-constexpr uint32_t kCkptVersion = 2;
+constexpr uint32_t kCkptVersion = 3;
 struct CkptWriter {
     std::vector<unsigned char> b;
     void u32(uint32_t v) { for (int i = 0; i < 4; i++) b.push_back((unsigned char)(v >> (8 * i))); }
@@ -1090,7 +1116,7 @@ struct CkptReader {
     uint64_t u64() { if (end - p < 8) { ok = false; return 0; } uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i); p += 8; return v; }
     float f32() { uint32_t v = u32(); float f; memcpy(&f, &v, 4); return f; }
 };
-constexpr size_t kCkptHeaderBytes = 8 + 4 * 2 + 8 + 4 * 3 + 4 * 2 + 4 + 8 + 4 * 3 + 8 * 4 + 4 + 8 * 2;   // 120
+constexpr size_t kCkptHeaderBytes = 8 + 4 * 2 + 8 + 4 * 3 + 4 * 2 + 4 + 8 + 4 * 4 + 8 * 4 + 4 + 8 * 2;   // 124
 }  // namespace
 
 int pmc_save_checkpoint(pmc_handle *h, const float *d_disk, const int16_t *d_n, uint64_t sweep, const char *path)
@@ -1107,7 +1133,7 @@ int pmc_save_checkpoint(pmc_handle *h, const float *d_disk, const int16_t *d_n, 
     wr.u32(kCkptVersion); wr.u32(PMC_NMAX);
     wr.u64((uint64_t)p.n_particles); wr.f32(p.phi); wr.f32(p.sigma_d); wr.f32(p.cell_w);
     wr.u32((uint32_t)p.nmax); wr.u32((uint32_t)p.n_M); wr.f32(p.move_delta); wr.u64(p.seed);
-    wr.u32((uint32_t)p.cps_multiple); wr.u32((uint32_t)p.rank); wr.u32((uint32_t)p.n_ranks);
+    wr.u32((uint32_t)p.cps_multiple); wr.u32((uint32_t)p.rank); wr.u32((uint32_t)p.n_ranks); wr.u32((uint32_t)p.proposal);
     wr.u64(sweep); wr.u64(trials); wr.u64(accepted); wr.u64(lost); wr.u32(status);
     const uint64_t disk_bytes = pmc_disk_bytes(h), n_bytes = pmc_n_bytes(h);
     wr.u64(disk_bytes); wr.u64(n_bytes);
@@ -1139,7 +1165,7 @@ int pmc_load_checkpoint(pmc_handle *h, const char *path, float *d_disk, int16_t 
     memset(&a, 0, sizeof(a));
     a.n_particles = (int64_t)rd.u64(); a.phi = rd.f32(); a.sigma_d = rd.f32(); a.cell_w = rd.f32();
     a.nmax = (int)rd.u32(); a.n_M = (int)rd.u32(); a.move_delta = rd.f32(); a.seed = rd.u64();
-    a.cps_multiple = (int)rd.u32(); a.rank = (int)rd.u32(); a.n_ranks = (int)rd.u32();
+    a.cps_multiple = (int)rd.u32(); a.rank = (int)rd.u32(); a.n_ranks = (int)rd.u32(); a.proposal = (int)rd.u32();
     const uint64_t sw = rd.u64(), trials = rd.u64(), accepted = rd.u64(), lost = rd.u64();
     const uint32_t status = rd.u32();
     const uint64_t disk_bytes = rd.u64(), n_bytes = rd.u64();
@@ -1147,7 +1173,7 @@ int pmc_load_checkpoint(pmc_handle *h, const char *path, float *d_disk, int16_t 
     if (!rd.ok || version != kCkptVersion || nmax_file != PMC_NMAX ||
         a.n_particles != b.n_particles || a.phi != b.phi || a.sigma_d != b.sigma_d || a.cell_w != b.cell_w ||
         a.nmax != b.nmax || a.n_M != b.n_M || a.move_delta != b.move_delta || a.seed != b.seed ||
-        a.cps_multiple != b.cps_multiple || a.rank != b.rank || a.n_ranks != b.n_ranks ||
+        a.cps_multiple != b.cps_multiple || a.rank != b.rank || a.n_ranks != b.n_ranks || a.proposal != b.proposal ||
         disk_bytes != pmc_disk_bytes(h) || n_bytes != pmc_n_bytes(h)) { fclose(fp); return PMC_E_INVALID; }
     std::vector<char> buf(disk_bytes + n_bytes);
     bool ok = fread(buf.data(), 1, buf.size(), fp) == buf.size();

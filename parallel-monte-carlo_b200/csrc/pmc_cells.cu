@@ -60,34 +60,41 @@ __device__ __forceinline__ int local_row(int gy, const DevGeom &g)
     return lr < g.local_rows ? lr : -1;
 }
 
-// pass 1: one thread per particle: cell id, atomic arrival rank, remember the particle index
-// Arrivals beyond the 8th go to a small global list, so that an overflowing cell keeps its 8
-// LOWEST particle indices (what a scan over atoms 0..N-1, start.cu:133-140, keeps when it stops
-// writing at nmax) whatever order the atomics resolve in.
-constexpr unsigned kOvfCap = 1u << 20;
-
+// pass 1: one thread per particle: cell id, arrival rank, remember the particle index.
+// Lanes of a warp that fall into the same cell (neighbours in the lattice order of init_r, or in the
+// cell-major order of disk_to_r) share ONE atomic: the lowest such lane reserves their slots, the others take
+// consecutive ranks in lane (= particle index) order.
+// Arrivals beyond the 8th go to a global list with room for every particle, so that an overflowing cell keeps
+// its 8 LOWEST particle indices (what a scan over atoms 0..N-1, start.cu:133-140, keeps when it stops
+// writing at nmax) whatever order the atomics resolve in and however many particles overflow.
 __global__ void assign_rank_kernel(const float *__restrict__ r, DevGeom g,
                                    unsigned *__restrict__ cnt32, unsigned *__restrict__ idx_tmp,
                                    uint2 *__restrict__ ovf, unsigned *__restrict__ ovf_count, Counters *ctr)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= g.n_particles) return;
-    float x = __ldg(r + i), y = __ldg(r + i + g.n_particles);
-    int cx = cell_of(x, g), cy = cell_of(y, g);
-    if (cx < 0 || cy < 0) {
-        if (g.row0 == 0 || g.wrap_y) atomicAdd(&ctr->lost, 1ull);   // counted once (rank 0)
-        atomicOr(&ctr->status, PMC_STATUS_LOST);
-        return;
+    long long cell = -1;
+    if (i < g.n_particles) {
+        float x = __ldg(r + i), y = __ldg(r + i + g.n_particles);
+        int cx = cell_of(x, g), cy = cell_of(y, g);
+        if (cx < 0 || cy < 0) {
+            if (g.row0 == 0 || g.wrap_y) atomicAdd(&ctr->lost, 1ull);   // counted once (rank 0)
+            atomicOr(&ctr->status, PMC_STATUS_LOST);
+        } else {
+            int lr = local_row(cy, g);
+            if (lr >= 0) cell = (long long)lr * g.cps + cx;
+        }
     }
-    int lr = local_row(cy, g);
-    if (lr < 0) return;
-    long long cell = (long long)lr * g.cps + cx;
-    unsigned s = atomicAdd(cnt32 + cell, 1u);
+    // warp-aggregated arrival rank (cells < 2^31: cps <= 46340)
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(0xffffffffu, (int)cell);
+    if (cell < 0) return;
+    const unsigned leader = __ffs(peers) - 1u, below = __popc(peers & ((1u << lane) - 1u));
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(cnt32 + cell, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned s = base + below;
     if (s < PMC_NMAX) idx_tmp[cell * PMC_NMAX + s] = (unsigned)i;
-    else {
-        const unsigned k = atomicAdd(ovf_count, 1u);
-        if (k < kOvfCap) ovf[k] = make_uint2((unsigned)cell, (unsigned)i);
-    }
+    else ovf[atomicAdd(ovf_count, 1u)] = make_uint2((unsigned)cell, (unsigned)i);
 }
 
 __device__ __forceinline__ void cswap(unsigned &a, unsigned &b)
@@ -129,7 +136,7 @@ __global__ void assign_fill_kernel(const float *__restrict__ r, DevGeom g,
     cswap(v[3], v[4]);
     if (c32 > PMC_NMAX) {
         // rare: merge the late arrivals, keep the 8 smallest indices (v stays sorted ascending)
-        const unsigned m = min(*ovf_count, kOvfCap);
+        const unsigned m = *ovf_count;
         for (unsigned k = 0; k < m; k++) {
             const uint2 e = ovf[k];
             if (e.x != (unsigned)cell || e.y >= v[7]) continue;
@@ -482,7 +489,8 @@ cudaError_t pmc_launch_assign(const DevGeom &g, const float *d_r, float4 *disk, 
     // cnt32[local_cells] is followed by the overflow-list counter (zeroed by the same memset)
     cudaError_t e = cudaMallocAsync(&cnt32, (local_cells + 1) * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    e = cudaMallocAsync(&ovf, (size_t)kOvfCap * sizeof(uint2), st);
+    // room for every particle: touched only by arrivals beyond the 8th of a cell, costs address space, not bandwidth
+    e = cudaMallocAsync(&ovf, (size_t)g.n_particles * sizeof(uint2), st);
     if (e != cudaSuccess) { cudaFreeAsync(cnt32, st); return e; }
     e = cudaMallocAsync(&idx_tmp, local_cells * PMC_NMAX * sizeof(unsigned), st);
     if (e != cudaSuccess) { cudaFreeAsync(cnt32, st); cudaFreeAsync(ovf, st); return e; }

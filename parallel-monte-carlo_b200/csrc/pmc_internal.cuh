@@ -26,6 +26,7 @@ struct DevGeom {
     int M;                  // move_delta / q: trial displacements are m * q, m in [-M, M]
     unsigned nM2;           // 2M + 1
     float mofs;             // 2^23 + M (exact): turns the biased mantissa trick into m
+    int proposal;           // PMC_PROPOSAL_UNIFORM / PMC_PROPOSAL_GAUSSIAN
     float L;
     float half_L;
     double L_box;
@@ -122,8 +123,12 @@ int pmc4_make_tensor_map(void *tmap_out128, const float4 *base, const Geom4 &g, 
 cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out,
                                unsigned *flags, unsigned epoch, cudaStream_t st);
 cudaError_t pmc4_launch_export(const Geom4 &g, int ghost, const float4 *in, float4 *disk, int16_t *n, cudaStream_t st);
+// slab ring: add the stamps (== epoch) of the received flag rows to flag rows row_lo.. / row_hi.. of `flags`
+cudaError_t pmc4_launch_flag_merge(unsigned *flags, const unsigned *recv_lo, int row_lo, const unsigned *recv_hi, int row_hi,
+                                   int nrows, int FW, unsigned epoch, cudaStream_t st);
 // tile rows [by0, by0 + nby) of one planned sweep (nby <= 0: all rows), optional second band
-// [by1, by1 + nby1) in the same launch; fast = 1: the 3-plane / 4-CTA kernel (boxes must not touch slab ghost rows)
+// [by1, by1 + nby1) in the same launch; fast = 1: the 3-plane / 4-CTA kernel (the crowded-cell flags under the box must
+// be valid: slab ghost rows get theirs through the ring)
 cudaError_t pmc4_launch_sweep(const Geom4 &g, const void *tmap_in, const void *tmap_half, float4 *dout, const SweepArgs &a,
                               Counters *ctr, cudaStream_t st, int fast, int by0 = 0, int nby = 0, int by1 = 0, int nby1 = 0);
 
@@ -172,6 +177,21 @@ __device__ __forceinline__ float grid_disp(uint32_t r, unsigned nM2, float mofs)
     uint32_t tb;
     asm("mad.hi.u32 %0, %1, %2, 1258291200;" : "=r"(tb) : "r"((r & 0xFFFFFF00u) | 0x80u), "r"(nM2));   // + 0x4B000000
     return __fadd_rn(__uint_as_float(tb), -mofs);
+}
+
+// The reference's Gaussian proposal (make_move subsweep.h:60-71: x + curand_normal * sigma per axis) in grid
+// units: Box-Muller on bits 8..30 of the two words, signs from bit 31 (oracle subsweep_cell, proposal == 1).
+__device__ __forceinline__ void gauss_disp(uint32_t ra, uint32_t rb, int M, float &mx, float &my)
+{
+    const float u1 = __fmul_rn(__fadd_rn((float)((ra >> 8) & 0x7FFFFFu), 0.5f), 1.1920928955078125e-07f);   // (0, 1)
+    const float u2 = __fmul_rn(__fadd_rn((float)((rb >> 8) & 0x7FFFFFu), 0.5f), 5.9604644775390625e-08f);   // (0, 1/2)
+    const float rr = __fmul_rn(__fsqrt_rn(__fmul_rn(-2.0f, logf(u1))), (float)M);
+    float sn, cs;
+    sincospif(u2, &sn, &cs);
+    mx = rintf(__fmul_rn(rr, cs));
+    my = rintf(__fmul_rn(rr, sn));
+    if (ra >> 31) mx = -mx;
+    if (rb >> 31) my = -my;
 }
 
 // ------------------------------------------------------------------ small helpers

@@ -443,8 +443,10 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
                     const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
                     const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-                    const float px = __fmaf_rn(grid_disp(rw[2 * s], g.nM2, g.mofs), dscale, x);     // make_move subsweep.h:60-71
-                    const float py = __fmaf_rn(grid_disp(rw[2 * s + 1], g.nM2, g.mofs), dscale, y);
+                    float mx = grid_disp(rw[2 * s], g.nM2, g.mofs), my = grid_disp(rw[2 * s + 1], g.nM2, g.mofs);
+                    if (g.proposal == PMC_PROPOSAL_GAUSSIAN) gauss_disp(rw[2 * s], rw[2 * s + 1], g.M, mx, my);
+                    const float px = __fmaf_rn(mx, dscale, x);     // make_move subsweep.h:60-71
+                    const float py = __fmaf_rn(my, dscale, y);
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
@@ -506,8 +508,10 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     float *fx = slot_ptr(it), *fy = fx + 2 * PL * 4;
                     it = (it + 1 >= cnt) ? 0 : it + 1;
                     const float x = *fx, y = *fy;
-                    const float px = __fmaf_rn(grid_disp(ra, g.nM2, g.mofs), dscale, x);
-                    const float py = __fmaf_rn(grid_disp(rb, g.nM2, g.mofs), dscale, y);
+                    float mx = grid_disp(ra, g.nM2, g.mofs), my = grid_disp(rb, g.nM2, g.mofs);
+                    if (g.proposal == PMC_PROPOSAL_GAUSSIAN) gauss_disp(ra, rb, g.M, mx, my);
+                    const float px = __fmaf_rn(mx, dscale, x);
+                    const float py = __fmaf_rn(my, dscale, y);
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     if (m >= 0.0f) {

@@ -750,7 +750,7 @@ __device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_
 
 // ---- one launch = one sweep.  FAST: 3 planes staged, 4 CTAs per SM, crowded tiles re-done in two or
 // three 4-plane pieces in the same shared memory.  !FAST: 4 planes, 3 CTAs per SM, no flag
-// lookup (slab boundary rows, whose ghost rows carry no flags).
+// lookup (pmc_set_tuning "four_plane": the A/B partner of the fast path; round 1 ran the slab boundary rows on it).
 template <int MINB, bool FAST>
 __global__ void __launch_bounds__(kNT, MINB)
 sweep4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
@@ -859,6 +859,15 @@ __global__ void export4_kernel(const float4 *__restrict__ in, float4 *__restrict
     v.z = s0 + 2 < cnt ? v.z : fill; v.w = s0 + 3 < cnt ? v.w : fill;
     disk[cell * 4 + ch] = v;
     if (ch == 0) n[cell] = (int16_t)cnt;
+}
+
+__global__ void flag_merge_kernel(unsigned *__restrict__ flags, const unsigned *__restrict__ recv_lo, int row_lo,
+                                  const unsigned *__restrict__ recv_hi, int row_hi, int nwords, int FW, unsigned epoch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    if (recv_lo[i] == epoch) flags[(size_t)row_lo * FW + i] = epoch;
+    if (recv_hi[i] == epoch) flags[(size_t)row_hi * FW + i] = epoch;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -978,6 +987,14 @@ int pmc4_make_tensor_map(void *tmap_out, const float4 *base, const Geom4 &g, int
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+cudaError_t pmc4_launch_flag_merge(unsigned *flags, const unsigned *recv_lo, int row_lo, const unsigned *recv_hi, int row_hi,
+                                   int nrows, int FW, unsigned epoch, cudaStream_t st)
+{
+    const int nwords = nrows * FW;
+    flag_merge_kernel<<<(nwords + 255) / 256, 256, 0, st>>>(flags, recv_lo, row_lo, recv_hi, row_hi, nwords, FW, epoch);
+    return cudaGetLastError();
 }
 
 cudaError_t pmc4_launch_import(const Geom4 &g, int ghost, const float4 *disk, const int16_t *n, float4 *out,

@@ -485,7 +485,7 @@ def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
     assert c["lost"] > 0 and c["status"] & 1
 
 
-@pytest.mark.parametrize("knob", ["force_crowded", "no_ns4", "full_halo", "generic", "bands1"])
+@pytest.mark.parametrize("knob", ["force_crowded", "no_ns4", "full_halo", "generic", "four_plane", "bands1"])
 def test_tuning_knobs_never_change_the_result(knob):
     """pmc_set_tuning chooses which kernel / schedule computes the sweep, never the result: "force_crowded"
     sends EVERY tile down the crowded-tile path (half-height pieces with all four planes staged), "full_halo"
@@ -665,3 +665,46 @@ def test_subsweep_acceptance_matches_the_reference_device_functions():
         d1, n1 = arrays(ep["n_after"], ep["disk_after"])
         assert np.array_equal(bits(got), bits(d1)) and np.array_equal(n.cpu().numpy(), n1)
     assert n_trials == 576
+
+
+# ---------------------------------------------------------------- the reference's Gaussian proposal (statistical parity)
+def test_gaussian_proposal_agrees_with_the_oracle_within_three_sigma():
+    """PMC_PROPOSAL_GAUSSIAN = the reference's make_move (subsweep.h:64: x + curand_normal * sigma).  It needs
+    logf / sincospif, which no CPU reproduces bit for bit, so this option is checked the way north_star asks for
+    the reference itself: acceptance ratio and contact value within 3 sigma over independent seeds.  Tolerance:
+    |mean_gpu - mean_cpu| < 3 sqrt(se_gpu^2 + se_cpu^2), se = standard error over 8 seeds."""
+    from oracle import oracle as O
+    import pmc_b200
+    N, burn, S = 4096, 150, 150
+    kw = dict(KW, move_delta=0.08)
+    acc = {"gpu": [], "cpu": []}
+    gc = {"gpu": [], "cpu": []}
+    for k in range(8):
+        mc = pmc_b200.ParallelMC(N, **dict(kw, seed=500 + k), proposal=1)
+        disk, n = mc.assign(mc.init_r())
+        mc.sweep(disk, n, 0, burn)
+        mc.reset_counters()
+        hist = np.zeros(256, dtype=np.uint64)
+        for s in range(10):
+            mc.sweep(disk, n, burn + s * (S // 10), S // 10)
+            hist += mc.gr_hist(disk, n, 2.0, 256)
+        c = mc.counters()
+        chk = mc.check(disk, n)
+        assert chk["overlaps"] == 0 and chk["min_d2"] >= 1.0 and chk["total"] == N and c["status"] == 0
+        acc["gpu"].append(c["accepted"] / c["trials"])
+        gc["gpu"].append(mc.pressure_from_hist(hist, 2.0, 10)[1])
+        o = O.Oracle(N, **dict(kw, seed=700 + k), proposal=1)       # independent seeds on the CPU side
+        od, on = o.assign(o.init_r())
+        o.sweep(od, on, 0, burn)
+        a0, t0 = o.accepted.value, o.trials.value
+        hist = np.zeros(256, dtype=np.uint64)
+        for s in range(10):
+            o.sweep(od, on, burn + s * (S // 10), S // 10)
+            hist += o.gr_hist(od, on, 2.0, 256)
+        acc["cpu"].append((o.accepted.value - a0) / (o.trials.value - t0))
+        gc["cpu"].append(mc.pressure_from_hist(hist, 2.0, 10)[1])
+    for name, v in (("acceptance", acc), ("g(sigma+)", gc)):
+        g_, c_ = np.array(v["gpu"]), np.array(v["cpu"])
+        se = np.sqrt(g_.var(ddof=1) / len(g_) + c_.var(ddof=1) / len(c_))
+        assert abs(g_.mean() - c_.mean()) < 3.0 * se, (name, g_.mean(), c_.mean(), se)
+    assert 0.15 < np.mean(acc["gpu"]) < 0.6

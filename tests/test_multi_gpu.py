@@ -91,15 +91,21 @@ def test_slab_geometry_on_one_gpu(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,sweeps,port", [(2 ** 18, 7, 29611),      # one launch per part and sweep
-                                           (2 ** 22, 9, 29612)])     # 542 rows per rank: interior in 5 bands on 5 streams
-def test_two_rank_run_is_bit_identical_to_single_gpu(built, N, sweeps, port):
+@pytest.mark.parametrize("N,sweeps,port,mode", [
+    (2 ** 18, 7, 29611, "dense"),       # one launch per part and sweep
+    (2 ** 22, 9, 29612, "dense"),       # 542 rows per rank: interior in 5 bands on 5 streams
+    (2 ** 20, 12, 29613, "crowded"),    # cells with 7 / 8 disks in the ghost rows: the flags that travel with the ring
+])
+def test_two_rank_run_is_bit_identical_to_single_gpu(built, N, sweeps, port, mode):
     import torch
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (run by hand with gpurun --gpus 2)")
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2; log kept under profiles/r2/)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "scripts", "slab_worker.py"), str(N), str(sweeps)]
+           os.path.join(ROOT, "scripts", "slab_worker.py"), str(N), str(sweeps)] + (["crowded"] if mode == "crowded" else [])
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "bit_identical=True" in out.stdout and "protocol_identical=True" in out.stdout
+    if mode == "crowded":
+        import re
+        assert int(re.search(r"crowded_cells=(\d+)", out.stdout).group(1)) > 20

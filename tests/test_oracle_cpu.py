@@ -493,3 +493,33 @@ def test_trial_probes_are_reproducible_from_the_generator():
         subprocess.check_call([sys.executable, "-c", code], stdout=subprocess.DEVNULL)
         for f in ("trial_probes.json", "trial_probes_in.txt"):
             assert open(os.path.join(td, f)).read() == open(os.path.join(HERE, "golden", f)).read(), f
+
+
+# ---------------------------------------------------------------- the reference's Gaussian proposal (option)
+def test_gaussian_proposal_is_normal_symmetric_and_keeps_the_invariants():
+    """proposal = 1: x + N(0, delta^2) per axis (make_move subsweep.h:64, curand_normal * sigma), on the grid."""
+    o = O.Oracle(4096, **dict(KW, move_delta=0.08), proposal=1)
+    disk, n = o.assign(o.init_r())
+    o.sweep(disk, n, 0, 20)
+    dx = []
+    for sweep in range(20, 30):
+        order, f, d = o.schedule(sweep)
+        for colour in order:
+            o.trace_on(4 * 1024)
+            o.subsweep(disk, n, o.colour_to_off(colour), sweep)
+            for r in o.trace_off():
+                dx.append((r.px - r.own_x[r.slot], r.py - r.own_y[r.slot]))
+        o.shift_cells(disk, n, f, d)
+    k = np.array(dx, dtype=np.float64) / float(o.g.dscale)
+    assert np.array_equal(k, np.rint(k))                        # displacements are whole grid steps
+    z = k / o.g.M
+    nz = len(z)
+    assert nz > 30000
+    for axis in (0, 1):
+        assert abs(z[:, axis].mean()) < 4.0 / np.sqrt(nz)
+        assert abs(z[:, axis].var() - 1.0) < 0.03
+        assert abs(np.mean(np.abs(z[:, axis]) < 1.0) - 0.6827) < 0.01
+    assert abs(np.mean(z[:, 0] * z[:, 1])) < 4.0 / np.sqrt(nz)  # the two axes are independent
+    o.sweep(disk, n, 30, 200)
+    chk = o.check(disk, n)
+    assert chk["total"] == 4096 and chk["overlaps"] == 0 and chk["min_d2"] >= 1.0 and o.lost == 0
