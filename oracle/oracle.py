@@ -210,3 +210,95 @@ class Oracle:
         lib().oracle_gr_hist(C.byref(self.g), _f(disk), _s(n), C.c_float(r_max), nbins,
                              h.ctypes.data_as(C.POINTER(C.c_uint64)))
         return h
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3-D Lennard-Jones mode (oracle/pmc_oracle_lj.c)
+class LjGeom(C.Structure):
+    _fields_ = [("n_particles", C.c_int64), ("n_cells", C.c_int64), ("cps", C.c_int), ("nmax", C.c_int), ("n_M", C.c_int),
+                ("proposal", C.c_int), ("L", C.c_float), ("half_L", C.c_float), ("w", C.c_float), ("rc2", C.c_float),
+                ("beta", C.c_float), ("sigma", C.c_float), ("dscale", C.c_float), ("seed", C.c_uint64)]
+
+
+def _lj():
+    L = lib()
+    if getattr(L, "_lj_ready", False):
+        return L
+    gp, fp, sp, u64p = C.POINTER(LjGeom), C.POINTER(C.c_float), C.POINTER(C.c_int16), C.POINTER(C.c_uint64)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.oracle_lj_make_geom.argtypes = [C.c_int64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_int, gp]
+    L.oracle_lj_init_r.argtypes = [gp, fp]
+    L.oracle_lj_assign.argtypes = [gp, fp, fp, sp]
+    L.oracle_lj_assign.restype = C.c_int64
+    L.pmc_lj_pair.argtypes = [C.c_float] * 4
+    L.pmc_lj_pair.restype = C.c_float
+    L.pmc_exp_det.argtypes = [C.c_float]
+    L.pmc_exp_det.restype = C.c_float
+    L.oracle_lj_subsweep.argtypes = [gp, fp, sp, ip, C.c_uint64, u64p, u64p, dp]
+    L.oracle_lj_shift_cells.argtypes = [gp, fp, sp, C.c_int, C.c_float]
+    L.oracle_lj_shift_cells.restype = C.c_int64
+    L.oracle_lj_schedule.argtypes = [gp, C.c_uint64, ip, ip, fp]
+    L.oracle_lj_colour_to_off.argtypes = [C.c_int, ip]
+    L.oracle_lj_sweep.argtypes = [gp, fp, sp, C.c_uint64, C.c_int, u64p, u64p, dp]
+    L.oracle_lj_sweep.restype = C.c_int64
+    L.oracle_lj_energy.argtypes = [gp, fp, sp]
+    L.oracle_lj_energy.restype = C.c_double
+    L.oracle_lj_probe.argtypes = [gp, fp, sp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, ip, fp, fp]
+    L._lj_ready = True
+    return L
+
+
+class OracleLJ:
+    """Host-side mirror of include/pmc_lj.h on top of the C oracle."""
+
+    def __init__(self, n_particles, L=10.0, beta=0.3, cells_per_side=4, nmax=10, n_M=10, sigma=0.5, seed=1234, proposal=0):
+        self.g = LjGeom()
+        if _lj().oracle_lj_make_geom(n_particles, L, beta, cells_per_side, nmax, n_M, sigma, seed, proposal, C.byref(self.g)):
+            raise ValueError("oracle_lj_make_geom failed")
+        self.trials, self.accepted, self.dE, self.lost = C.c_uint64(0), C.c_uint64(0), C.c_double(0.0), 0
+
+    def init_r(self):
+        r = np.zeros((3, self.g.n_particles), dtype=np.float32)
+        if _lj().oracle_lj_init_r(C.byref(self.g), _f(r)):
+            raise ValueError("n_particles is not a perfect cube")
+        return r
+
+    def assign(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float32)
+        disk = np.zeros((self.g.n_cells, 3, self.g.nmax), dtype=np.float32)
+        n = np.zeros(self.g.n_cells, dtype=np.int16)
+        self.lost += _lj().oracle_lj_assign(C.byref(self.g), _f(r), _f(disk), _s(n))
+        return disk, n
+
+    def subsweep(self, disk, n, off, sweep):
+        _lj().oracle_lj_subsweep(C.byref(self.g), _f(disk), _s(n), (C.c_int * 3)(*off), sweep, C.byref(self.trials),
+                                 C.byref(self.accepted), C.byref(self.dE))
+
+    def shift_cells(self, disk, n, f, d):
+        self.lost += _lj().oracle_lj_shift_cells(C.byref(self.g), _f(disk), _s(n), f, C.c_float(d))
+
+    def schedule(self, sweep):
+        order, f, d = (C.c_int * 8)(), C.c_int(), C.c_float()
+        _lj().oracle_lj_schedule(C.byref(self.g), sweep, order, C.byref(f), C.byref(d))
+        return list(order), f.value, np.float32(d.value)
+
+    @staticmethod
+    def colour_to_off(colour):
+        o = (C.c_int * 3)()
+        _lj().oracle_lj_colour_to_off(colour, o)
+        return [o[0], o[1], o[2]]
+
+    def sweep(self, disk, n, sweep0, n_sweeps):
+        tr = np.zeros(max(n_sweeps, 1), dtype=np.float64)
+        self.lost += _lj().oracle_lj_sweep(C.byref(self.g), _f(disk), _s(n), sweep0, n_sweeps, C.byref(self.trials),
+                                           C.byref(self.accepted), tr.ctypes.data_as(C.POINTER(C.c_double)))
+        return tr[:n_sweeps]
+
+    def energy(self, disk, n):
+        return float(_lj().oracle_lj_energy(C.byref(self.g), _f(disk), _s(n)))
+
+    def probe(self, disk, n, cx, cy, cz, slot, px, py, pz):
+        oob, ec, en = C.c_int(), C.c_float(), C.c_float()
+        _lj().oracle_lj_probe(C.byref(self.g), _f(disk), _s(n), cx, cy, cz, slot, C.c_float(px), C.c_float(py), C.c_float(pz),
+                              C.byref(oob), C.byref(ec), C.byref(en))
+        return oob.value, np.float32(ec.value), np.float32(en.value)

@@ -19,8 +19,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PMC_LIB_PATH") or os.path.join(_HERE, "libpmc_b200.so")     # the override is a development aid
-SOURCES = ["pmc_api.cu", "pmc_cells.cu", "pmc_sweep.cu", "pmc_sweep4.cu"]
-HEADERS = ["pmc_internal.cuh", os.path.join("..", "..", "include", "pmc.h")]
+SOURCES = ["pmc_api.cu", "pmc_cells.cu", "pmc_sweep.cu", "pmc_sweep4.cu", "pmc_lj.cu"]
+HEADERS = ["pmc_internal.cuh", os.path.join("..", "..", "include", "pmc.h"), os.path.join("..", "..", "include", "pmc_lj.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -383,3 +383,143 @@ class ParallelMC:
 
     def exchange_ghosts(self, disk, n):
         _ck(lib().pmc_exchange_ghosts(self._h, disk.data_ptr(), n.data_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3-D Lennard-Jones mode (include/pmc_lj.h): the reference's actual physics behind the same call sites
+class LjParams(C.Structure):
+    _fields_ = [("n_particles", C.c_int64), ("L", C.c_float), ("beta", C.c_float), ("cells_per_side", C.c_int),
+                ("nmax", C.c_int), ("n_M", C.c_int), ("sigma", C.c_float), ("seed", C.c_uint64),
+                ("proposal", C.c_int), ("device", C.c_int)]
+
+
+LJ_EXPORTS = ["pmc_lj_create", "pmc_lj_destroy", "pmc_lj_r_bytes", "pmc_lj_disk_bytes", "pmc_lj_n_bytes", "pmc_lj_set_stream",
+              "pmc_lj_init_r", "pmc_lj_assign", "pmc_lj_subsweep", "pmc_lj_shift_cells", "pmc_lj_schedule",
+              "pmc_lj_colour_to_off", "pmc_lj_sweep", "pmc_lj_energy", "pmc_lj_get_counters", "pmc_lj_reset_counters",
+              "pmc_lj_disk_to_r_host"]
+
+
+def _lj_lib():
+    L = lib()
+    if getattr(L, "_lj_ready", False):
+        return L
+    hp, vp = C.c_void_p, C.c_void_p
+    L.pmc_lj_create.argtypes = [C.POINTER(LjParams), C.POINTER(hp)]
+    L.pmc_lj_destroy.argtypes = [hp]
+    for f in ("pmc_lj_r_bytes", "pmc_lj_disk_bytes", "pmc_lj_n_bytes"):
+        getattr(L, f).argtypes = [hp]
+        getattr(L, f).restype = C.c_size_t
+    L.pmc_lj_set_stream.argtypes = [hp, vp]
+    L.pmc_lj_init_r.argtypes = [hp, vp]
+    L.pmc_lj_assign.argtypes = [hp, vp, vp, vp]
+    L.pmc_lj_subsweep.argtypes = [hp, vp, vp, C.POINTER(C.c_int), C.c_uint64]
+    L.pmc_lj_shift_cells.argtypes = [hp, vp, vp, C.c_int, C.c_float]
+    L.pmc_lj_schedule.argtypes = [hp, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    L.pmc_lj_colour_to_off.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    L.pmc_lj_colour_to_off.restype = None
+    L.pmc_lj_sweep.argtypes = [hp, vp, vp, C.c_uint64, C.c_int, vp]
+    L.pmc_lj_energy.argtypes = [hp, vp, vp, C.POINTER(C.c_double)]
+    L.pmc_lj_get_counters.argtypes = [hp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    L.pmc_lj_reset_counters.argtypes = [hp]
+    L.pmc_lj_disk_to_r_host.argtypes = [hp, vp, vp, vp, C.POINTER(C.c_int64)]
+    L._lj_ready = True
+    return L
+
+
+class ParallelMCLJ:
+    """3-D Lennard-Jones handle: the reference's own arrays (r [3][N], disk [cells][3][nmax] global
+    coordinates, int16 n) and call sites (start.cu:212,227,242-245,255), V2 energy accounting."""
+    strict = True
+    last_warning = 0
+
+    def __init__(self, n_particles, L=10.0, beta=0.3, cells_per_side=4, nmax=10, n_M=10, sigma=0.5, seed=1234,
+                 proposal=0, device=-1):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("parallel-monte-carlo_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.params = LjParams(n_particles, L, beta, cells_per_side, nmax, n_M, sigma, seed, proposal, device)
+        self._h = C.c_void_p()
+        _ck(_lj_lib().pmc_lj_create(C.byref(self.params), C.byref(self._h)))
+        self.device = torch.device("cuda", torch.cuda.current_device() if device < 0 else device)
+        self.n_cells = cells_per_side ** 3
+        _ck(_lj_lib().pmc_lj_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def close(self):
+        if self._h:
+            _lj_lib().pmc_lj_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ckw(self, rc):
+        if rc in (-3, -4) and not self.strict:
+            self.last_warning = rc
+            return
+        _ck(rc)
+
+    def alloc_cells(self):
+        t = self.torch
+        return (t.zeros((self.n_cells, 3, self.params.nmax), dtype=t.float32, device=self.device),
+                t.zeros((self.n_cells,), dtype=t.int16, device=self.device))
+
+    def init_r(self):
+        r = self.torch.empty((3, self.params.n_particles), dtype=self.torch.float32, device=self.device)
+        _ck(_lj_lib().pmc_lj_init_r(self._h, r.data_ptr()))
+        return r
+
+    def assign(self, r):
+        disk, n = self.alloc_cells()
+        self._ckw(_lj_lib().pmc_lj_assign(self._h, r.data_ptr(), disk.data_ptr(), n.data_ptr()))
+        return disk, n
+
+    def subsweep(self, disk, n, off, sweep):
+        o = (C.c_int * 3)(*off)
+        self._ckw(_lj_lib().pmc_lj_subsweep(self._h, disk.data_ptr(), n.data_ptr(), o, sweep))
+
+    def shift_cells(self, disk, n, f, d):
+        self._ckw(_lj_lib().pmc_lj_shift_cells(self._h, disk.data_ptr(), n.data_ptr(), f, C.c_float(d)))
+
+    def schedule(self, sweep):
+        order, f, d = (C.c_int * 8)(), C.c_int(), C.c_float()
+        _ck(_lj_lib().pmc_lj_schedule(self._h, sweep, order, C.byref(f), C.byref(d)))
+        return list(order), f.value, d.value
+
+    @staticmethod
+    def colour_to_off(colour):
+        o = (C.c_int * 3)()
+        _lj_lib().pmc_lj_colour_to_off(colour, o)
+        return [o[0], o[1], o[2]]
+
+    def sweep(self, disk, n, sweep0, n_sweeps, trace=False):
+        """n_sweeps x (8 sub-sweeps + shiftCells); trace=True returns the accepted energy change of every sweep."""
+        import numpy as np
+        tr = np.zeros(max(n_sweeps, 1), dtype=np.float64) if trace else None
+        self._ckw(_lj_lib().pmc_lj_sweep(self._h, disk.data_ptr(), n.data_ptr(), sweep0, n_sweeps,
+                                         tr.ctypes.data if trace else None))
+        return tr[:n_sweeps] if trace else None
+
+    def energy(self, disk, n):
+        e = C.c_double()
+        _ck(_lj_lib().pmc_lj_energy(self._h, disk.data_ptr(), n.data_ptr(), C.byref(e)))
+        return e.value
+
+    def counters(self):
+        tr, ac, lo, st, de = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_double()
+        _ck(_lj_lib().pmc_lj_get_counters(self._h, C.byref(tr), C.byref(ac), C.byref(lo), C.byref(st), C.byref(de)))
+        return {"trials": tr.value, "accepted": ac.value, "lost": lo.value, "status": st.value, "dE": de.value}
+
+    def reset_counters(self):
+        _ck(_lj_lib().pmc_lj_reset_counters(self._h))
+
+    def disk_to_r_host(self, disk, n):
+        import numpy as np
+        r = np.zeros((3, self.params.n_particles), dtype=np.float32)
+        k = C.c_int64()
+        _ck(_lj_lib().pmc_lj_disk_to_r_host(self._h, disk.data_ptr(), n.data_ptr(), r.ctypes.data, C.byref(k)))
+        return r, k.value

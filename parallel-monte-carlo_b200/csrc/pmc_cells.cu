@@ -60,39 +60,29 @@ __device__ __forceinline__ int local_row(int gy, const DevGeom &g)
     return lr < g.local_rows ? lr : -1;
 }
 
-// pass 1: one thread per particle: cell id, arrival rank, remember the particle index.
-// Lanes of a warp that fall into the same cell (neighbours in the lattice order of init_r, or in the
-// cell-major order of disk_to_r) share ONE atomic: the lowest such lane reserves their slots, the others take
-// consecutive ranks in lane (= particle index) order.
+// pass 1: one thread per particle: cell id, atomic arrival rank, remember the particle index.
 // Arrivals beyond the 8th go to a global list with room for every particle, so that an overflowing cell keeps
 // its 8 LOWEST particle indices (what a scan over atoms 0..N-1, start.cu:133-140, keeps when it stops
 // writing at nmax) whatever order the atomics resolve in and however many particles overflow.
+// (Measured and rejected: warp-aggregated ranks through __match_any_sync, 236 us instead of 120 us at
+// N = 2^24 - the match costs more than the one atomic per lane it saves; profiles/r2.)
 __global__ void assign_rank_kernel(const float *__restrict__ r, DevGeom g,
                                    unsigned *__restrict__ cnt32, unsigned *__restrict__ idx_tmp,
                                    uint2 *__restrict__ ovf, unsigned *__restrict__ ovf_count, Counters *ctr)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long cell = -1;
-    if (i < g.n_particles) {
-        float x = __ldg(r + i), y = __ldg(r + i + g.n_particles);
-        int cx = cell_of(x, g), cy = cell_of(y, g);
-        if (cx < 0 || cy < 0) {
-            if (g.row0 == 0 || g.wrap_y) atomicAdd(&ctr->lost, 1ull);   // counted once (rank 0)
-            atomicOr(&ctr->status, PMC_STATUS_LOST);
-        } else {
-            int lr = local_row(cy, g);
-            if (lr >= 0) cell = (long long)lr * g.cps + cx;
-        }
+    if (i >= g.n_particles) return;
+    float x = __ldg(r + i), y = __ldg(r + i + g.n_particles);
+    int cx = cell_of(x, g), cy = cell_of(y, g);
+    if (cx < 0 || cy < 0) {
+        if (g.row0 == 0 || g.wrap_y) atomicAdd(&ctr->lost, 1ull);   // counted once (rank 0)
+        atomicOr(&ctr->status, PMC_STATUS_LOST);
+        return;
     }
-    // warp-aggregated arrival rank (cells < 2^31: cps <= 46340)
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned peers = __match_any_sync(0xffffffffu, (int)cell);
-    if (cell < 0) return;
-    const unsigned leader = __ffs(peers) - 1u, below = __popc(peers & ((1u << lane) - 1u));
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(cnt32 + cell, (unsigned)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const unsigned s = base + below;
+    int lr = local_row(cy, g);
+    if (lr < 0) return;
+    long long cell = (long long)lr * g.cps + cx;
+    unsigned s = atomicAdd(cnt32 + cell, 1u);
     if (s < PMC_NMAX) idx_tmp[cell * PMC_NMAX + s] = (unsigned)i;
     else ovf[atomicAdd(ovf_count, 1u)] = make_uint2((unsigned)cell, (unsigned)i);
 }

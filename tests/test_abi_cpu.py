@@ -33,6 +33,18 @@ def test_library_builds_loads_and_exports_everything(built):
     assert sorted(pmc_b200.EXPORTS) == declared_symbols()
 
 
+def test_lj_header_symbols_are_exported(built):
+    """include/pmc_lj.h (3-D Lennard-Jones mode): every declared entry point is exported by the same library."""
+    import re
+    import pmc_b200
+    L = pmc_b200.lib()
+    txt = open(os.path.join(ROOT, "include", "pmc_lj.h")).read()
+    names = sorted(set(re.findall(r"\b(pmc_lj_\w+)\s*\(", txt)))
+    assert names == sorted(pmc_b200.LJ_EXPORTS)
+    for s in names:
+        assert hasattr(L, s), s
+
+
 def test_library_is_sm100a_sass_with_packed_fp32(built):
     import pmc_b200
     out = subprocess.run(["cuobjdump", "-sass", pmc_b200.LIB_PATH], capture_output=True, text=True).stdout

@@ -1,0 +1,130 @@
+"""3-D Lennard-Jones mode, CPU side: the oracle (oracle/pmc_oracle_lj.c) against what the REFERENCE's own
+kernels and device functions computed on a B200 (tests/golden/ref_kernels_seed*.json: assign kernel.cu:92-150 and
+V2 shiftCells shiftCells.h:23-112 are 3-D kernels; tests/golden/ref_trials.json: out_of_bound, calculate_energy_in_cell,
+calculate_energy_in_neighbors subsweep.h:73-172), plus the internal consistency of the energy accounting."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("seed", list(range(1, 17)))
+def test_lj_assign_and_shift_cells_equal_the_reference_kernels_in_3d(seed):
+    """Same arrays, same coordinates as the reference (global, [cell][3][nmax], nmax = 30): every cell, every slot,
+    every step bit for bit - crowded seeds included, nothing is truncated in this mode."""
+    gold = json.load(open(os.path.join(HERE, "golden", f"ref_kernels_seed{seed}.json")))
+    p = gold["params"]
+    o = O.OracleLJ(p["n_real"], L=10.0, cells_per_side=4, nmax=30)
+    assert o.g.w == 2.5
+    r = np.array(gold["r"], dtype=np.float32)
+    disk, n = o.assign(r)
+
+    def same(step):
+        np.testing.assert_array_equal(n.astype(np.int64), np.array(step["n"], dtype=np.int64))
+        for c in range(64):
+            if n[c] == 0:
+                assert str(c) not in step["cells"]
+                continue
+            ref = np.array(step["cells"][str(c)], dtype=np.float32)
+            assert np.array_equal(bits(disk[c, :, :n[c]]), bits(ref)), (c, disk[c, :, :n[c]], ref)
+    same(gold["steps"][0])
+    assert o.lost == p["n_real"] - sum(gold["steps"][0]["n"])       # the lower box face is outside (kernel.cu:134)
+    for step in gold["steps"][1:]:
+        o.shift_cells(disk, n, step["f"], np.float32(step["d"]))
+        same(step)
+
+
+def test_lj_energies_and_bounds_equal_the_reference_device_functions():
+    """oracle_lj_probe (the two terms of calculate_new_energy, subsweep.h:186-191) against the reference's own
+    calculate_energy_in_cell / calculate_energy_in_neighbors with all particles present, on the 916 probes of
+    tests/golden/trial_probes.json.  The reference evaluates sqrtf + __powf(dist, -6), this path 1 / r^2: the
+    tolerance is 2e-5 relative to the sum of the |pair energies| (powf.approx is good to ~1e-6 per pair)."""
+    ref = json.load(open(os.path.join(HERE, "golden", "ref_trials.json")))["probes"]
+    probes = json.load(open(os.path.join(HERE, "golden", "trial_probes.json")))["probes"]
+    it = iter(open(os.path.join(HERE, "golden", "trial_probes_in.txt")).read().split("\n"))
+    states = []
+    for _ in range(int(next(it))):
+        st = {}
+        for _ in range(int(next(it))):
+            t = next(it).split()
+            c, k = int(t[0]), int(t[1])
+            st[c] = (np.array(t[2:2 + k], dtype=np.float32), np.array(t[2 + k:2 + 2 * k], dtype=np.float32))
+        states.append(st)
+    o = O.OracleLJ(64, L=10.0, cells_per_side=4, nmax=10)
+    n_checked = n_big = 0
+    for p, r in zip(probes, ref):
+        disk = np.zeros((64, 3, 10), dtype=np.float32)
+        n = np.zeros(64, dtype=np.int16)
+        for c, (gx, gy) in states[p["state"]].items():
+            n[c] = len(gx)
+            disk[c, 0, :len(gx)], disk[c, 1, :len(gx)], disk[c, 2, :len(gx)] = gx, gy, np.float32(-3.75)
+        cell = p["cx"] + 4 * p["cy"]
+        own = np.array(p["own"], dtype=np.float32)
+        ox, oy = np.float32(p["cx"] * 2.5 - 5.0), np.float32(p["cy"] * 2.5 - 5.0)
+        n[cell] = len(own)
+        disk[cell, 0, :len(own)], disk[cell, 1, :len(own)], disk[cell, 2, :len(own)] = own[:, 0] + ox, own[:, 1] + oy, np.float32(-3.75)
+        px, py = np.float32(p["px"]) + ox, np.float32(p["py"]) + oy
+        oob, ec, en = o.probe(disk, n, p["cx"], p["cy"], 0, p["slot"], px, py, np.float32(-3.75))
+        lower_face = np.float32(p["px"]) == 0.0 or np.float32(p["py"]) == 0.0
+        assert bool(oob) == (bool(r["oob"]) or lower_face)          # closed interval in the reference
+        # scale of the sum: sum of |pair energies| is not available from the harness; use max(|E|, e_max, 1)
+        scale = max(abs(r["e_full_cell"]) + abs(r["e_full_nbrs"]), abs(r["e_max"]), 1.0)
+        n_big += scale > 1e4        # proposals deep inside a core: the same relative tolerance holds
+        assert abs(float(ec) - r["e_full_cell"]) <= 2e-5 * scale, (p, r, ec)
+        assert abs(float(en) - r["e_full_nbrs"]) <= 2e-5 * scale, (p, r, en)
+        n_checked += 1
+    assert n_checked == 916 and n_big > 20
+
+
+def test_lj_pair_energy_cutoff_minimum_and_deterministic_exp():
+    L = O._lj()
+    assert L.pmc_lj_pair(1.0, 0.0, 0.0, 6.25) == 0.0                         # r = 1 = sigma
+    assert abs(L.pmc_lj_pair(2.0 ** (1.0 / 6.0), 0.0, 0.0, 6.25) + 1.0) < 1e-6   # minimum -epsilon at 2^(1/6)
+    assert L.pmc_lj_pair(2.5, 0.0, 0.0, 6.25) != 0.0 and L.pmc_lj_pair(2.5001, 0.0, 0.0, 6.25) == 0.0   # r <= w kept
+    assert L.pmc_lj_pair(0.9, 0.0, 0.0, 6.25) > 0.0
+    xs = -np.concatenate([np.linspace(0, 5, 2001), np.linspace(5, 86, 500)])
+    err = max(abs(L.pmc_exp_det(float(x)) / math.exp(float(np.float32(x))) - 1.0) for x in xs)
+    assert err < 4e-7
+    assert L.pmc_exp_det(0.0) == 1.0 and L.pmc_exp_det(-100.0) == 0.0
+
+
+@pytest.mark.parametrize("N,L,cps,nmax,n_M", [(64, 10.0, 4, 10, 10), (1000, 10.0, 4, 30, 15)])
+def test_lj_energy_trace_matches_the_total_energy(N, L, cps, nmax, n_M):
+    """V2 accounting (kernel.cu:642-643,672-680): E(lattice) + sum of accepted dE == calc_energy of the final state.
+    (64, 10, 4, 10, 10) is start.cu's own #define block, (1000, ..., 30, 15) the benchmark run of the slides."""
+    o = O.OracleLJ(N, L=L, cells_per_side=cps, nmax=nmax, n_M=n_M)
+    disk, n = o.assign(o.init_r())
+    e0 = o.energy(disk, n)
+    tr = o.sweep(disk, n, 0, 40)
+    e1 = o.energy(disk, n)
+    assert o.lost == 0 and int(n.sum()) == N
+    assert abs((e0 + tr.sum()) - e1) < 1e-3 * max(1.0, abs(e1))
+    assert 0.0 < o.accepted.value / o.trials.value < 1.0
+    # every particle is inside its cell (half-open) and no slot beyond n is used by the energy
+    w, cx = o.g.w, np.arange(cps ** 3) % cps
+    for c in range(cps ** 3):
+        k = n[c]
+        lb = np.float32(cx[c] * w - L / 2)
+        assert np.all(disk[c, 0, :k] > lb) and np.all(disk[c, 0, :k] <= lb + np.float32(w) + 1e-6)
+
+
+def test_lj_schedule_ranges_and_colours():
+    o = O.OracleLJ(64)
+    seen_f, seen_first = set(), set()
+    for s in range(600):
+        order, f, d = o.schedule(s)
+        assert sorted(order) == list(range(8)) and f in (0, 1, 2) and -o.g.w / 2 < d <= o.g.w / 2
+        seen_f.add(f)
+        seen_first.add(order[0])
+    assert seen_f == {0, 1, 2} and seen_first == set(range(8))
+    assert [O.OracleLJ.colour_to_off(c) for c in (0, 1, 2, 4, 7)] == [[0, 0, 0], [0, 0, 1], [0, 1, 0], [1, 0, 0], [1, 1, 1]]
