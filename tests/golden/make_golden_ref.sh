@@ -19,3 +19,5 @@ for s in 11 12 13 14; do ./oracle/_ref/ref_harness $s 44 14 > "$out/ref_kernels_
 for s in 15 16; do ./oracle/_ref/ref_harness $s 52 18 > "$out/ref_kernels_seed$s.json"; done
 # the sub-sweep device functions of subsweep.h on the probes of tests/golden/make_trial_probes.py
 ./oracle/_ref/ref_harness_v1 < tests/golden/trial_probes_in.txt > "$out/ref_trials.json"
+# a short 3-D Lennard-Jones run made of the reference's own device functions / kernels (bug-fixed loop)
+./oracle/_ref/ref_harness_lj 16 300 200 > "$out/ref_lj_stats.json"

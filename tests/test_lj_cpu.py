@@ -128,3 +128,35 @@ def test_lj_schedule_ranges_and_colours():
         seen_first.add(order[0])
     assert seen_f == {0, 1, 2} and seen_first == set(range(8))
     assert [O.OracleLJ.colour_to_off(c) for c in (0, 1, 2, 4, 7)] == [[0, 0, 0], [0, 0, 1], [0, 1, 0], [1, 0, 0], [1, 1, 1]]
+
+
+def test_lj_oracle_statistics_match_a_run_of_the_reference_device_functions():
+    """tests/golden/ref_lj_stats.json: 8 short runs (512 particles, L = 10, beta = 0.3, sigma = 0.5, n_M = 10) made of
+    the reference's own make_move / accept_move / energy functions (subsweep.h), assign and V2 shiftCells in a
+    bug-fixed loop on a B200 (oracle/ref_harness_lj.cu).  The oracle with the Gaussian proposal samples the same
+    ensemble: acceptance ratio and energy per particle within 3 sigma over seeds."""
+    ref = json.load(open(os.path.join(HERE, "golden", "ref_lj_stats.json")))
+    p = ref["params"]
+    assert (p["N_ATOMS"], p["L"], p["beta"], p["cellsPerSide"], p["nmax"], p["n_M"], p["sigma"]) == (512, 10, 0.3, 4, 30, 10, 0.5)
+    burn, sample = p["burn_sweeps"], p["sample_sweeps"]
+    acc, en = [], []
+    for seed in range(2000, 2016):
+        o = O.OracleLJ(512, L=10.0, beta=0.3, cells_per_side=4, nmax=30, n_M=10, sigma=0.5, seed=seed, proposal=1)
+        disk, n = o.assign(o.init_r())
+        o.sweep(disk, n, 0, burn)
+        a0, t0 = o.accepted.value, o.trials.value
+        es = []
+        for b in range(sample // 10):
+            o.sweep(disk, n, burn + 10 * b, 10)
+            es.append(o.energy(disk, n) / 512)
+        acc.append((o.accepted.value - a0) / (o.trials.value - t0))
+        en.append(np.mean(es))
+        assert o.lost == 0
+    for mine, key in ((np.array(acc), "acceptance"), (np.array(en), "energy_per_particle")):
+        theirs = np.array([r[key] for r in ref["runs"]])
+        assert len(theirs) >= 16
+        # pooled per-seed variance (same ensemble, same protocol): a sample variance from 8 runs alone is off by
+        # a factor 3 either way often enough to make a 3 sigma test meaningless
+        var = (((mine - mine.mean()) ** 2).sum() + ((theirs - theirs.mean()) ** 2).sum()) / (len(mine) + len(theirs) - 2)
+        se = np.sqrt(var / len(mine) + var / len(theirs))
+        assert abs(mine.mean() - theirs.mean()) < 3.0 * se, (key, mine.mean(), theirs.mean(), se)
