@@ -63,6 +63,7 @@ struct SweepArgs {
     // computed (4 bits per colour, >= 1)
     int tx, ty, hx, hy;
     unsigned lo_x, lo_y;
+    int sh_nseg, sh_inv, sh_inv2;   // shift_store_pass: kNT / tx and the multiply-shift reciprocals of tx and of kNT / tx
     // per colour, everything about "which cells are active" that does not depend on the tile (tiles start
     // on even columns / rows): bits 0-3 i0, 4-7 j0 (first active column / row of the region), 8-11 / 12-15
     // lo_x / lo_y, 16-23 / 24-31 chunk offset of the first active cell / of its left neighbour in the staged

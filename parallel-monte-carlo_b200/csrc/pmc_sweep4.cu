@@ -180,14 +180,14 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
 {
     constexpr unsigned PS = PLC * 16;
     unsigned sa = scell, step = 8;                      // next free slot; the walk alternates +8 / +PS-8
-    const unsigned lim = scell + NPL * PS;
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         const float fc = F == 0 ? f4get(own.x03, own.x47, i) : f4get(own.y03, own.y47, i);
         const float oc = F == 0 ? f4get(own.y03, own.y47, i) : f4get(own.x03, own.x47, i);
         const float D = __fadd_rn(fc, -d);
         // unused x slots hold the sentinel and fail on their own; unused y slots hold 0 / the count
-        if ((F == 0 || i < own.cnt) && D > 0.0f && D <= w) {    // shiftCells.h:62
+        const bool stay = (F == 0 || i < own.cnt) & (D > 0.0f) & (D <= w);      // shiftCells.h:62
+        if (stay) {
             sts_pair(sa, F == 0 ? D : oc, F == 0 ? oc : D);
             sa += step; step = PS - step;
         }
@@ -200,9 +200,10 @@ __device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRe
         const float fc = F == 0 ? f4get(up.x03, up.x47, i) : f4get(up.y03, up.y47, i);
         const float oc = F == 0 ? f4get(up.y03, up.y47, i) : f4get(up.x03, up.x47, i);
         const float D = __fadd_rn(fc, -d);
-        if (i < up.cnt && !(D > 0.0f && D <= w)) {              // shiftCells.h:94
-            const float Ds = __fadd_rn(D, sshift);              // shiftCells.h:97
-            sts_pair(sa < lim ? sa : sdump, F == 0 ? Ds : oc, F == 0 ? oc : Ds);
+        const float Ds = __fadd_rn(D, sshift);                  // shiftCells.h:97
+        const bool imm = (i < up.cnt) & !((D > 0.0f) & (D <= w));              // shiftCells.h:94
+        if (imm) {
+            sts_pair(min(sa, sdump), F == 0 ? Ds : oc, F == 0 ? oc : Ds);      // sdump lies behind every slot of the tile
             sa += step; step = PS - step;
         }
     }
@@ -229,10 +230,10 @@ __device__ __noinline__ void crowded_cell_out(float4 *dout, unsigned *flag_out, 
 
 // fast path, rare: a cell ends up with 7 or 8 disks (or more: dropped), but slots 6 and 7 exist only
 // in HBM.  Finds the immigrants that did not fit (the `first` earlier ones are placed), writes the
-// cell's P3 chunk to HBM, stamps the crowded-cell flags and leaves the sign of y5 set for the store.
+// cell's P3 chunk to HBM (the caller then skips its own P3 store) and stamps the crowded-cell flags.
 // Deliberately not inlined: nothing of it may cost the common path a register.
 __device__ __noinline__ int shift_overflow3(int F, float4 ux03, float2 ux45, float4 uy03, float2 uy45, int ucnt,
-                                            float d, float w, float sshift, int first, int n_total, float *y5,
+                                            float d, float w, float sshift, int first, int n_total,
                                             int owned, float4 *dout, const Geom4 *gp, const SweepArgs *ap,
                                             int X, int Y)
 {
@@ -253,7 +254,6 @@ __device__ __noinline__ int shift_overflow3(int F, float4 ux03, float2 ux45, flo
     }
     const int n = n_total < PMC_NMAX ? n_total : PMC_NMAX;
     if (n < PMC_NMAX) p3.w = __int_as_float(n);
-    *y5 = -*y5;                                         // "P3 of this cell is already in HBM"
     if (owned)
         crowded_cell_out(dout, ap->flag_out, ap->epoch_out, gp->cps, gp->rows, gp->wrap_y, gp->CH, gp->FW, X, Y, 1, p3);
     return n_total - n;                                 // dropped
@@ -269,12 +269,13 @@ struct TileCtx {
     int X0, Y0;             // internal array coordinates of region (0, 0)
     int tx, ty;             // nominal owned extent of this tiling
     int wraps;              // the region reaches beyond the box: global cell coordinates need the periodic wrap
+    int edge;               // owned cells of this tile have periodic images in the margins
 };
 
 // ---- one colour: one thread per active cell (subsweep.h:242-245), own cell in registers
 template <int NS, typename TL>
 __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
-                                            int k, int aq, int bq, unsigned &my_trials, unsigned &my_acc)
+                                            int k, int aq, int bq, unsigned &my_cnt)
 {
     constexpr int PITCH = TL::PITCH, PLC = TL::PLC;
     const int cps = g.cps;
@@ -381,7 +382,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
             if (s == 3) { ox[1] = w1 ? px : ox[1]; oy[1] = w1 ? py : oy[1]; }
         }
     }
-    if (owned) { my_trials += 4u; my_acc += n_acc; }
+    if (owned) my_cnt += (4u << 16) + n_acc;     // trials in the high half, accepted in the low half (<= 64 per thread)
     // cpy_D_sh_to_Disk subsweep.h:29-36 (shuffled order is written back, like the reference)
     float4 *pown = reinterpret_cast<float4 *>(cown);
     pown[0] = make_float4(ox[0], ox[1], ox[2], ox[3]);
@@ -390,179 +391,157 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     if (NS == 8) pown[3 * PLC] = make_float4(ox[6], ox[7], oy[6], oy[7]);
 }
 
-// ---- shiftCells(f, d) of this sweep for the owned cells, in place (pair order out)
+// ---- shiftCells(f, d) of this sweep for the owned cells and their way to HBM, in ONE pass (v11; v4-v10 had a
+// shift pass that left the tile in shared memory and a separate store pass).  One thread per destination cell:
+// V2 shiftCells.h:23-112 scatters the stayers of `own` and the immigrants from `up` into the cell's own staged
+// chunks in pair order (shift_into_tile), the same thread reads the three chunks back, turns them into
+// P0..P2 in registers (+ the in-band count and the "5 or more" flag, + the constant P3 of the fast path) and stores
+// them: no second pass over the tile, no second barrier, no count / flag round trip through shared memory.
+// Lanes run along x in both cases, so a warp stores runs of TX/2 consecutive float4 per parity.
+//   F = 1 (shift along y): thread = (segment of K rows, column); it walks its segment from the upstream end and
+//     keeps the raw cell u+1 in registers as `up` of cell u.  The raw cell beyond the segment belongs to another
+//     warp: it is read before the one CTA barrier of this pass.
+//   F = 0 (shift along x): warp = segment of K rows, lane = column; `up` is the neighbour lane's cell of the same
+//     row, so all hazards are inside the warp: __syncwarp() between the reads and the writes of a row, no
+//     CTA barrier at all.
 template <int NS, typename TL, int NPL, int F>
-__device__ __forceinline__ void shift_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
-                                           float4 *__restrict__ dout, int sdir, int tid, Counters *ctr)
+__device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
+                                                 float4 *__restrict__ dout, int sdir, float d, int tid, Counters *ctr)
 {
-    const int TX = t.tx, TY = t.ty;
     constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
-    const float d = a.shift_d, w = g.w;
-    const float sshift = __fmul_rn(w, (float)sdir);                 // shiftCells.h:84-86
-    // One thread owns a strip of K consecutive owned cells along the shift axis (cell 0 at the
-    // downstream end) and walks it from the upstream end down: before the barrier it reads its
-    // last cell and the raw cell after the strip (first cell of the next strip, or the extra
-    // upstream row / column); cell u is then rewritten with raw u as `own` and raw u+1, still
-    // in registers, as `up`.  Only two cells are ever live in registers.
-    const int SEG1 = kNT / TX, K1 = (TY + SEG1 - 1) / SEG1;         // f = 1: column strips of K1 rows
-    constexpr int SEG0 = 8;                                         // f = 0: row strips of K0 columns (TY <= 32 rows of 8 threads)
-    const int K0 = (TX + SEG0 - 1) / SEG0;
-    constexpr int KMAX = 4;                                         // TX <= 32, TY <= 32: 8 strips of at most 4 cells
-    int i0, j0, len;
-    const int di = F == 0 ? sdir : 0, dj = F == 0 ? 0 : sdir;
-    if (F == 1) {
-        const int seg = tid / TX, col = tid - seg * TX, k0 = seg * K1;
-        len = (seg < SEG1 && k0 < TY) ? min(K1, TY - k0) : 0;
-        i0 = t.ox0 + col; j0 = t.oy0 + (sdir > 0 ? k0 : TY - 1 - k0);
-    } else {
-        const int row = tid / SEG0, seg = tid - row * SEG0, k0 = seg * K0;
-        len = (row < TY && k0 < TX) ? min(K0, TX - k0) : 0;
-        j0 = t.oy0 + row; i0 = t.ox0 + (sdir > 0 ? k0 : TX - 1 - k0);
-    }
+    constexpr unsigned PS = PLC * 16;
+    const int TX = t.tx, TY = t.ty;
+    const float w = g.w;
+    const float sshift = sdir > 0 ? w : -w;                         // shiftCells.h:84-86
+    const unsigned sdump = smem_u32(sm + (NPL - 1) * PLC + TL::PLB);    // padding behind the last staged plane
+    const long long ps = (long long)2 * g.CH;                       // float4 chunks between planes
+    const long long rstride = 4 * ps;                               // ... between internal rows
+
     auto cell_ptr = [&](int i, int j) -> float4 * {
         const int is = i + t.xs;
         return sm + j * PITCH + (is & 1) * HB + (is >> 1);
     };
-    auto load_cell = [&](int i, int j, CellRegs &c) {           // P0..P3 -> plain x / y registers
-        const float4 *p = cell_ptr(i, j);
-        const float4 p0 = p[0], p1 = p[PLC];
+    auto load_cell = [&](int i, int j, CellRegs &c) {               // P0..P3 -> plain x / y registers
+        const unsigned sp = smem_u32(cell_ptr(i, j));
+        const float4 p0 = lds128<0>(sp), p1 = lds128<PS>(sp);
         c.x03 = p0; c.y03 = make_float4(p1.x, p1.y, p1.z, fabsf(p1.w));
         if (NS == 8) {
-            const float4 p2 = p[2 * PLC], p3 = p[3 * PLC];
+            const float4 p2 = lds128<2 * PS>(sp), p3 = lds128<(NPL == 4 ? 3 : 2) * PS>(sp);
             c.x47 = make_float4(p2.x, p2.y, p3.x, p3.y); c.y47 = make_float4(p2.z, p2.w, p3.z, p3.w);
             c.cnt = decode_cnt8(p3);
-        } else {
-            // NS = 6 / 4: the higher slots are known to be unused in this tile
-            const float4 p2 = p[2 * PLC];
-            c.x47 = NS == 6 ? make_float4(p2.x, p2.y, kSent, kSent) : make_float4(kSent, kSent, kSent, kSent);
-            c.y47 = NS == 6 ? make_float4(p2.z, p2.w, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (NS == 6) {               // the higher slots are known to be unused in this tile
+            const float4 p2 = lds128<2 * PS>(sp);
+            c.x47 = make_float4(p2.x, p2.y, kSent, kSent);
+            c.y47 = make_float4(p2.z, p2.w, 0.f, 0.f);
             c.cnt = decode_cnt6(p2);
+        } else {
+            // NS = 4: no cell of the tile holds more than 4 disks; the count is in the bits of y5
+            const float4 p2 = lds128<2 * PS>(sp);
+            c.x47 = make_float4(kSent, kSent, kSent, kSent);
+            c.y47 = make_float4(0.f, 0.f, 0.f, 0.f);
+            c.cnt = __float_as_int(p2.w);
         }
     };
-    const unsigned sdump = smem_u32(sm + PLC + TL::PLB);            // 16 unused bytes behind plane 1
-    CellRegs cur, upc;
-    if (len > 0) {
-        load_cell(i0 + (len - 1) * di, j0 + (len - 1) * dj, cur);
-        load_cell(i0 + len * di, j0 + len * dj, upc);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int v = 0; v < KMAX; v++) {
-        const int u = len - 1 - v;
-        if (u >= 0) {
-            const int i = i0 + u * di, j = j0 + u * dj;
-            float4 *p = cell_ptr(i, j);
-            const float4 empty2 = make_float4(kSent, 0.f, kSent, 0.f);      // two unused slots in pair order
-#pragma unroll
-            for (int c = 0; c < NPL; c++) p[c * PLC] = empty2;
-            int n_own, dropped = 0;
-            int nNew = shift_into_tile<NS, F, NPL, PLC>(cur, upc, d, w, sshift, smem_u32(p), sdump, n_own);
-            // in-band counts and flags, pair order: y3 = chunk 1 word 3, y5 = chunk 2 word 3, y7 = chunk 3 word 3
-            float *fw = reinterpret_cast<float *>(p);
-            const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
-            if (nNew > 2 * NPL) {                       // rare: more disks than staged slots
-                if (NPL == 3) {
-                    constexpr int PSI = PLC * 16;
-                    const int placed_own = 2 * (n_own / PSI) + ((n_own % PSI) ? 1 : 0);
-                    dropped = shift_overflow3(F, upc.x03, make_float2(upc.x47.x, upc.x47.y), upc.y03,
-                                              make_float2(upc.y47.x, upc.y47.y), upc.cnt, d, w, sshift, 2 * NPL - placed_own,
-                                              nNew, fw + 2 * PLC * 4 + 3, owned, dout, &g, &a, t.X0 + i, t.Y0 + j);
-                } else dropped = nNew - 2 * NPL;
-                nNew -= dropped;
-            }
-            if (nNew >= 5) fw[PLC * 4 + 3] = -fw[PLC * 4 + 3];              // "5 or more" flag: sign of y3
-            if (nNew < 6) fw[2 * PLC * 4 + 3] = __int_as_float(nNew);
-            if (NPL == 4) {
-                if (nNew < PMC_NMAX) fw[3 * PLC * 4 + 3] = __int_as_float(nNew);
-                if (nNew >= 7 && owned)
-                    crowded_cell_out(dout, a.flag_out, a.epoch_out, g.cps, g.rows, g.wrap_y, g.CH, g.FW,
-                                     t.X0 + i, t.Y0 + j, 0, make_float4(0.f, 0.f, 0.f, 0.f));
-            }
+    // one destination cell: scatter, read back, store
+    auto emit = [&](int i, int j, const CellRegs &own, const CellRegs &up) {
+        const unsigned sp = smem_u32(cell_ptr(i, j));
+        const float4 empty2 = make_float4(kSent, 0.f, kSent, 0.f);  // two unused slots in pair order
+        sts128<0>(sp, empty2); sts128<PS>(sp, empty2); sts128<2 * PS>(sp, empty2);
+        if (NPL == 4) sts128<3 * PS>(sp, empty2);
+        int n_own;
+        int nNew = shift_into_tile<NS, F, NPL, PLC>(own, up, d, w, sshift, sp, sdump, n_own);
+        const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
+        const int X = t.X0 + i, Y = t.Y0 + j;
+        bool p3_done = false;
+        if (nNew > 2 * NPL) {                           // rare: more disks than staged slots
+            int dropped;
+            if (NPL == 3) {
+                const int placed_own = 2 * (n_own / (int)PS) + ((n_own % (int)PS) ? 1 : 0);
+                dropped = shift_overflow3(F, up.x03, make_float2(up.x47.x, up.x47.y), up.y03,
+                                          make_float2(up.y47.x, up.y47.y), up.cnt, d, w, sshift, 2 * NPL - placed_own,
+                                          nNew, owned, dout, &g, &a, X, Y);
+                p3_done = true;                         // P3 of this cell is already in HBM
+            } else dropped = nNew - 2 * NPL;
+            nNew -= dropped;
             if (dropped) {
                 atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
                 if (owned) atomicAdd(&ctr->lost, (unsigned long long)dropped);
             }
-            if (u > 0) {
-                upc = cur;
-                load_cell(i - di, j - dj, cur);
-            }
         }
-    }
-    __syncthreads();
-}
-
-// ---- owned cells -> HBM (+ periodic images into the margins).  thread -> fixed (chunk column h,
-// parity, plane pair), rows strided: a warp stores runs of TX/2 consecutive float4.  After the
-// shift the staged cells are in pair order and are converted to P0..P3 here: the thread of plane
-// pair 0 reads chunks 0, 1 and writes P0, P1; the thread of pair 1 reads chunks 2 (, 3), writes P2, P3.
-template <typename TL, int NPL>
-__device__ __forceinline__ void store_pass(const float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
-                                           float4 *__restrict__ dout, bool pair_order, int col0, int row0, int tid)
-{
-    constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
-    const int HX = t.tx / 2;
-    const int RSTEP = kNT / (4 * HX);                              // threads beyond RSTEP * 4 * HX do not store
-    const int cps = g.cps;
-    const int h = tid % HX, pr = (tid / HX) & 1, pp = (tid / (2 * HX)) & 1, rg = tid / (4 * HX);
-    const int ox = 2 * h + pr;                                      // owned column (parity == internal column parity)
-    const int ux = col0 + ox, uy0 = row0;
-    if (!(ox < t.nox && rg < RSTEP)) return;
-    const int is = t.ox0 + ox + t.xs;
-    unsigned src = smem_u32(sm + (is & 1) * HB + (is >> 1) + (t.oy0 + rg) * PITCH + 2 * pp * PLC);
-    const long long ps = (long long)2 * g.CH;                       // float4 chunks between planes
-    const long long rstride = 4 * ps;                               // ... between internal rows
-    float4 *dst = dout + ((long long)(kMY + uy0 + rg) * 4 + 2 * pp) * ps + (long long)pr * g.CH + ((kMX + ux) >> 1);
-    // periodic image of this column inside the margins (cps is even: parity is kept)
-    const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);
-    const bool yedge = g.wrap_y && (uy0 < kMY || uy0 + t.noy > g.rows - kMY);
-    // one cell: the two planes of this thread's pair (q1 unset: the shift already put P3 into HBM)
-    auto fetch = [&](float4 &q0, float4 &q1) -> bool {
-        const float4 c0 = lds128<0>(src);
-        float4 c1 = make_float4(kSent, kSent, 0.f, 0.f);
-        if (NPL == 4 || pp == 0) c1 = lds128<PLC * 16>(src);
-        bool q1_valid = true;
-        if (pp == 0) {
-            q0 = pair_order ? make_float4(c0.x, c0.z, c1.x, c1.z) : c0;
-            q1 = pair_order ? make_float4(c0.y, c0.w, c1.y, c1.w) : c1;
-        } else {
-            q0 = pair_order ? make_float4(c0.x, c0.z, c0.y, c0.w) : c0;
-            if (NPL == 4) q1 = pair_order ? make_float4(c1.x, c1.z, c1.y, c1.w) : c1;
-            else {
-                // fast path: at most 6 disks came in; 7 or 8 can go out only through the shift,
-                // which then wrote P3 itself and left the sign of y5 set
-                if (q0.y < kSentTest && q0.w < 0.0f) { q0.w = -q0.w; q1_valid = false; }
-                q1 = make_float4(kSent, kSent, 0.f, __int_as_float(decode_cnt6(q0)));
-            }
+        if (NPL == 4 && nNew >= 7 && owned)
+            crowded_cell_out(dout, a.flag_out, a.epoch_out, g.cps, g.rows, g.wrap_y, g.CH, g.FW, X, Y, 0,
+                             make_float4(0.f, 0.f, 0.f, 0.f));
+        // pair order -> P0..P3, in-band counts and the "5 or more" flag (sign of y3)
+        const float4 c0 = lds128<0>(sp), c1 = lds128<PS>(sp), c2 = lds128<2 * PS>(sp);
+        const float4 q0 = make_float4(c0.x, c0.z, c1.x, c1.z);
+        const float4 q1 = make_float4(c0.y, c0.w, c1.y, nNew >= 5 ? -c1.w : c1.w);
+        const float4 q2 = make_float4(c2.x, c2.z, c2.y, nNew < 6 ? __int_as_float(nNew) : c2.w);
+        float4 q3 = make_float4(kSent, kSent, 0.f, __int_as_float(nNew));
+        if (NPL == 4) {
+            const float4 c3 = lds128<3 * PS>(sp);
+            q3 = make_float4(c3.x, c3.z, c3.y, nNew < PMC_NMAX ? __int_as_float(nNew) : c3.w);
         }
-        return q1_valid;
-    };
-    if (!ximg && !yedge && pair_order) {
-#pragma unroll 2
-        for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
-            float4 q0, q1;
-            const bool v1 = fetch(q0, q1);
-            dst[0] = q0;
-            if (NPL == 4 || v1) dst[ps] = q1;
-            src += RSTEP * PITCH * 16; dst += RSTEP * rstride;
-        }
-    } else {
-#pragma unroll 1
-        for (int oyy = rg; oyy < t.noy; oyy += RSTEP) {
-            float4 q0, q1;
-            const bool v1 = fetch(q0, q1);
-            const int uy = uy0 + oyy;
-            // counts do not change without a shift: the flag of a crowded cell is carried over
-            if (NPL == 4 && !pair_order && pp == 1 && q1.x < kSentTest)
-                crowded_cell_out(dout, a.flag_out, a.epoch_out, cps, g.rows, g.wrap_y, g.CH, g.FW, kMX + ux, kMY + uy, 0, q1);
+        if (!owned) return;
+        float4 *dst = dout + ((long long)(Y * 4) * 2 + (X & 1)) * g.CH + (X >> 1);
+        dst[0] = q0; dst[ps] = q1; dst[2 * ps] = q2;
+        if (!p3_done) dst[3 * ps] = q3;
+        if (t.edge) {                                   // CTA-uniform: periodic images into the margins
+            const int ux = X - kMX, uy = Y - kMY, cps = g.cps;
+            const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);   // cps is even: parity is kept
             const int yimg = g.wrap_y ? (uy < kMY ? g.rows : (uy >= g.rows - kMY ? -g.rows : 0)) : 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
+#pragma unroll 1
+            for (int q = 1; q < 4; q++) {
                 if (((q & 1) && !ximg) || ((q & 2) && !yimg)) continue;
                 float4 *di = dst + ((q & 1) ? ximg : 0) + ((q & 2) ? (long long)yimg * rstride : 0);
-                di[0] = q0;
-                if (NPL == 4 || v1) di[ps] = q1;
+                di[0] = q0; di[ps] = q1; di[2 * ps] = q2;
+                if (!p3_done) di[3 * ps] = q3;
             }
-            src += RSTEP * PITCH * 16; dst += RSTEP * rstride;
+        }
+    };
+
+    if (F == 1) {
+        // column strips: nseg = kNT / TX segments of K rows; (seg, col) by an exact multiply-shift (tid < 256)
+        const int seg = (tid * a.sh_inv) >> 16, col = tid - seg * TX;
+        const int K = ((TY + a.sh_nseg - 1) * a.sh_inv2) >> 16, k0 = seg * K;      // ceil(TY / nseg)
+        const int len = seg < a.sh_nseg ? min(K, TY - k0) : 0;
+        const int i = t.ox0 + col;
+        const int jb = t.oy0 + (sdir > 0 ? k0 : TY - 1 - k0);       // cell u of the strip = row jb + u * sdir
+        CellRegs A, B;
+        if (len > 0) {
+            load_cell(i, jb + (len - 1) * sdir, A);
+            load_cell(i, jb + len * sdir, B);
+        }
+        __syncthreads();
+        int u = len - 1;
+#pragma unroll 1
+        for (int it = 0; it < 2; it++) {                // K <= 4: two ping-pong steps per iteration, no register copies
+            if (u >= 0) {
+                emit(i, jb + u * sdir, A, B);
+                if (u > 0) load_cell(i, jb + (u - 1) * sdir, B);
+            }
+            u--;
+            if (u >= 0) {
+                emit(i, jb + u * sdir, B, A);
+                if (u > 0) load_cell(i, jb + (u - 1) * sdir, A);
+            }
+            u--;
+        }
+    } else {
+        const int seg = tid >> 5, col = tid & 31;
+        const int K = (TY + kNT / 32 - 1) / (kNT / 32), k0 = seg * K;
+        const int len = min(K, TY - k0);                // warp-uniform
+        const bool active = col < TX;
+        const int i = t.ox0 + col;
+#pragma unroll 1
+        for (int v = 0; v < len; v++) {
+            const int j = t.oy0 + k0 + v;
+            CellRegs A, B;
+            if (active) {
+                load_cell(i, j, A);
+                load_cell(i + sdir, j, B);
+            }
+            __syncwarp();
+            if (active) emit(i, j, A, B);
         }
     }
 }
@@ -576,7 +555,7 @@ template <typename TL, int NPL>
 __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *__restrict__ dout, const Geom4 &g,
                                              const SweepArgs &a, Counters *ctr, int col0, int row0, int tx, int ty,
                                              float4 *sm, uint64_t *mbar, unsigned phase, bool prefetch,
-                                             unsigned &my_trials, unsigned &my_acc)
+                                             unsigned &my_cnt)
 {
     constexpr int PLC = TL::PLC, NAX = TL::NAX;
     const int tid = threadIdx.x;
@@ -599,6 +578,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     t.nox = min(tx, cps - col0); t.noy = min(ty, g.rows - row0);
     const int Xb0 = t.X0 - t.xs;                    // first column of the staged box
     t.wraps = t.rx0 < 0 || t.rx0 + t.RX > cps || g.row0 + t.ry0 < 0 || g.row0 + t.ry0 + t.RY > cps;
+    t.edge = col0 < kMX || col0 + tx > cps - kMX || (g.wrap_y && (row0 < kMY || row0 + ty > g.rows - kMY));
 
     // ------------------------------------------------------------ stage the tile: one TMA box per plane
     if (tid == 0) {
@@ -668,47 +648,46 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
         if (ns4) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                colour_pass<4, TL>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                colour_pass<4, TL>(sm, t, g, a, k, aq, bq, my_cnt);
                 __syncthreads();
             }
         } else if (!ns8) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                colour_pass<6, TL>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                colour_pass<6, TL>(sm, t, g, a, k, aq, bq, my_cnt);
                 __syncthreads();
             }
         } else if (NPL == 4) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                colour_pass<8, TL>(sm, t, g, a, k, aq, bq, my_trials, my_acc);
+                colour_pass<8, TL>(sm, t, g, a, k, aq, bq, my_cnt);
                 __syncthreads();
             }
         }
     }
 
-    // ------------------------------------------------------------ this sweep's shiftCells, owned cells only
-    if (do_shift) {
-        if (a.shift_f == 0) {
-            if (ns4) shift_pass<4, TL, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (!ns8) shift_pass<6, TL, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (NPL == 4) shift_pass<8, TL, NPL, 0>(sm, t, g, a, dout, sdir, tid, ctr);
+    // ------------------------------------------------------------ this sweep's shiftCells + owned tile -> HBM
+    // (no shift = a shift by d = 0: every disk stays, nothing immigrates)
+    {
+        const float d = do_shift ? a.shift_d : 0.0f;
+        if (a.shift_f == 0 || !do_shift) {
+            if (ns4) shift_store_pass<4, TL, NPL, 0>(sm, t, g, a, dout, sdir, d, tid, ctr);
+            else if (!ns8) shift_store_pass<6, TL, NPL, 0>(sm, t, g, a, dout, sdir, d, tid, ctr);
+            else if (NPL == 4) shift_store_pass<8, TL, NPL, 0>(sm, t, g, a, dout, sdir, d, tid, ctr);
         } else {
-            if (ns4) shift_pass<4, TL, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (!ns8) shift_pass<6, TL, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
-            else if (NPL == 4) shift_pass<8, TL, NPL, 1>(sm, t, g, a, dout, sdir, tid, ctr);
+            if (ns4) shift_store_pass<4, TL, NPL, 1>(sm, t, g, a, dout, sdir, d, tid, ctr);
+            else if (!ns8) shift_store_pass<6, TL, NPL, 1>(sm, t, g, a, dout, sdir, d, tid, ctr);
+            else if (NPL == 4) shift_store_pass<8, TL, NPL, 1>(sm, t, g, a, dout, sdir, d, tid, ctr);
         }
     }
-
-    // ------------------------------------------------------------ owned tile -> HBM
-    if (!PMC_DBG_BIT(a, 4)) store_pass<TL, NPL>(sm, t, g, a, dout, do_shift, col0, row0, tid);
     return false;
 }
 
 // acceptance counts reduced warp-level, one atomic per warp (kernel.cu:228,413 accept_counter)
-__device__ __forceinline__ void flush_counters(Counters *ctr, unsigned my_trials, unsigned my_acc)
+__device__ __forceinline__ void flush_counters(Counters *ctr, unsigned my_cnt)
 {
-    my_trials = __reduce_add_sync(0xffffffffu, my_trials);
-    my_acc = __reduce_add_sync(0xffffffffu, my_acc);
+    const unsigned my_trials = __reduce_add_sync(0xffffffffu, my_cnt >> 16);
+    const unsigned my_acc = __reduce_add_sync(0xffffffffu, my_cnt & 0xFFFFu);
     if ((threadIdx.x & 31) == 0 && my_trials) {
         atomicAdd(&ctr->trials, (unsigned long long)my_trials);
         atomicAdd(&ctr->accepted, (unsigned long long)my_acc);
@@ -717,8 +696,8 @@ __device__ __forceinline__ void flush_counters(Counters *ctr, unsigned my_trials
 
 // ---- crowded tile (a staged cell holds 7 or 8 disks): all four planes, half the rows at a time, in the
 // shared memory of the fast tile.  Rare, and deliberately NOT inlined: the fast path keeps its own
-// register allocation (64 registers without spills).  Returns (trials << 32) | accepted of this thread.
-__device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_half, float4 *dout, const Geom4 *gp,
+// register allocation (64 registers without spills).  Returns (trials << 16) | accepted of this thread.
+__device__ __noinline__ unsigned crowded_tile(const CUtensorMap *tmap_half, float4 *dout, const Geom4 *gp,
                                                         const SweepArgs *ap, Counters *ctr, int col0, int row0,
                                                         float4 *sm, uint64_t *mbar_fast)
 {
@@ -730,7 +709,7 @@ __device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    unsigned my_trials = 0, my_acc = 0;
+    unsigned my_cnt = 0;
     // rows a half-height box can own: its kSYBH rows hold the halo on both sides and the upstream row
     const int tyh = (kSYBH - 1 - 2 * ap->hy) & ~1;
     unsigned phase = 0;
@@ -739,13 +718,13 @@ __device__ __noinline__ unsigned long long crowded_tile(const CUtensorMap *tmap_
         const int ty = min(tyh, ap->ty - r);
         if (row0 + r < gp->rows) {
             process_tile<BoxH, 4>(tmap_half, dout, *gp, *ap, ctr, col0, row0 + r, ap->tx, ty, sm, mbar2, phase, false,
-                                  my_trials, my_acc);
+                                  my_cnt);
             phase ^= 1u;
         }
         __syncthreads();                        // every thread is done with the tile before the next box lands on it
         if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    return ((unsigned long long)my_trials << 32) | my_acc;
+    return my_cnt;
 }
 
 // ---- one launch = one sweep.  FAST: 3 planes staged, 4 CTAs per SM, crowded tiles re-done in two or
@@ -766,14 +745,13 @@ sweep4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     // tile row (a launch may cover one or two bands of rows)
     const int tby = (int)blockIdx.y < a.by_n1 ? (int)blockIdx.y + a.by_off : (int)blockIdx.y - a.by_n1 + a.by_off2;
     const int col0 = (int)blockIdx.x * a.tx, row0 = tby * a.ty;
-    unsigned my_trials = 0, my_acc = 0;
+    unsigned my_cnt = 0;
     if (!FAST) {
-        process_tile<BoxF, 4>(&tmap, dout, g, a, ctr, col0, row0, a.tx, a.ty, sm, mbar, 0u, true, my_trials, my_acc);
-    } else if (process_tile<BoxF, 3>(&tmap, dout, g, a, ctr, col0, row0, a.tx, a.ty, sm, mbar, 0u, true, my_trials, my_acc)) {
-        const unsigned long long r = crowded_tile(&tmap_half, dout, &g, &a, ctr, col0, row0, sm, mbar);
-        my_trials += (unsigned)(r >> 32); my_acc += (unsigned)r;
+        process_tile<BoxF, 4>(&tmap, dout, g, a, ctr, col0, row0, a.tx, a.ty, sm, mbar, 0u, true, my_cnt);
+    } else if (process_tile<BoxF, 3>(&tmap, dout, g, a, ctr, col0, row0, a.tx, a.ty, sm, mbar, 0u, true, my_cnt)) {
+        my_cnt += crowded_tile(&tmap_half, dout, &g, &a, ctr, col0, row0, sm, mbar);
     }
-    flush_counters(ctr, my_trials, my_acc);
+    flush_counters(ctr, my_cnt);
 }
 
 // ------------------------------------------------------------------ caller layout <-> internal layout
@@ -951,6 +929,11 @@ void pmc4_plan_sweep(SweepArgs &a, int full_halo)
     // rows: region ty + 2 hy + ey <= kSYB
     a.tx = (34 - 2 * a.hx - ex) & ~1;
     a.ty = (kSYB - 2 * a.hy - ey) & ~1;
+    // shift_store_pass, shift along y: thread -> (segment, column) = (tid / tx, tid % tx) and rows per segment
+    // = ceil(ty / nseg) by exact multiply-shifts (tid < 256, ty + nseg <= 64)
+    a.sh_nseg = kNT / a.tx;
+    a.sh_inv = 65536 / a.tx + 1;
+    a.sh_inv2 = 65536 / a.sh_nseg + 1;
 }
 
 int pmc4_tile_rows(const Geom4 &g, const SweepArgs &a) { return (g.rows + a.ty - 1) / a.ty; }

@@ -1,6 +1,6 @@
 """Ad-hoc timing of the fused sweep (development aid; bench.py is the contract)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import pmc_b200
 
