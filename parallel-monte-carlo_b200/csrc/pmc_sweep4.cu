@@ -161,55 +161,43 @@ __device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float np
     return m;
 }
 
-// V2 shiftCells.h:23-112 for one destination cell.  The result is scattered in place into the
-// staged tile in PAIR order: chunk c of the cell (plane c) = (x_2c, y_2c, x_2c+1, y_2c+1), so
-// that one 8-byte store places a disk and the slot -> address walk is two adds (+8, then
-// +plane stride - 8, alternating); the store phase converts to P0..P3 on the way out.
-// NPL = 3 (fast path, P3 not staged): slots 6 and 7 do not exist in shared memory; the rare
-// immigrants that land there are returned in `ext` (P3 layout) and go straight to HBM.
-// cb points at the first byte of the destination cell's first chunk.
+// V2 shiftCells.h:23-112.  The new content of a destination cell - the stayers of the cell itself in slot
+// order, then the immigrants from the cell upstream in slot order - is scattered into the cell's own staged
+// chunks in PAIR order: chunk c (plane c) = (x_2c, y_2c, x_2c+1, y_2c+1), so that one 8-byte store places a
+// disk and the slot -> address walk is two adds (+8, then +plane stride - 8, alternating); the way out to HBM
+// converts to P0..P3 in registers.
 __device__ __forceinline__ void sts_pair(unsigned saddr, float x, float y)
 {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(x), "f"(y) : "memory");
 }
 
-// returns the number of disks that WANT to be in the cell (more than 2 * NPL: the caller takes the rare path)
-template <int NS, int F, int NPL, int PLC>
-__device__ __forceinline__ int shift_into_tile(const CellRegs &own, const CellRegs &up, float d, float w,
-                                               float sshift, unsigned scell, unsigned sdump, int &n_own)
+// One source cell, one of the two roles.  STAY: its disks that remain (shiftCells.h:62: 0 < D <= w with D = c - d
+// along axis F) go to the walk position (sa, step) of their own cell.  !STAY: its disks that leave (shiftCells.h:94)
+// go, re-based by sshift (shiftCells.h:97), to the walk position of the cell downstream; that walk may run past
+// the last staged plane (7 or more disks want to be in the cell: rare), those stores land on a dump word behind
+// every slot of the tile, so that the final position still counts every disk.  `on` switches a lane off.
+// A slot is in use iff its x is not the sentinel (the unused y slots hold 0 or the in-band count).
+template <int NS, int F, bool STAY>
+__device__ __forceinline__ void walk_scatter(const CellRegs &c, bool on, float d, float w, float sshift,
+                                             unsigned &sa, unsigned &step, unsigned PS, unsigned sdump)
 {
-    constexpr unsigned PS = PLC * 16;
-    unsigned sa = scell, step = 8;                      // next free slot; the walk alternates +8 / +PS-8
 #pragma unroll
     for (int i = 0; i < NS; i++) {
-        const float fc = F == 0 ? f4get(own.x03, own.x47, i) : f4get(own.y03, own.y47, i);
-        const float oc = F == 0 ? f4get(own.y03, own.y47, i) : f4get(own.x03, own.x47, i);
-        const float D = __fadd_rn(fc, -d);
-        // unused x slots hold the sentinel and fail on their own; unused y slots hold 0 / the count
-        const bool stay = (F == 0 || i < own.cnt) & (D > 0.0f) & (D <= w);      // shiftCells.h:62
-        if (stay) {
-            sts_pair(sa, F == 0 ? D : oc, F == 0 ? oc : D);
+        const float xi = f4get(c.x03, c.x47, i), yi = f4get(c.y03, c.y47, i);
+        const float D = __fadd_rn(F == 0 ? xi : yi, -d);
+        const bool inside = (D > 0.0f) & (D <= w);
+        // F = 0: an unused x slot holds the sentinel and is not `inside` on its own
+        const bool used = xi < kSentTest;
+        const bool p = on & (STAY ? ((F == 0 || used) & inside) : (used & !inside));
+        const float Dn = STAY ? D : __fadd_rn(D, sshift);
+        if (p) {
+            sts_pair(STAY ? sa : min(sa, sdump), F == 0 ? Dn : xi, F == 0 ? yi : Dn);
             sa += step; step = PS - step;
         }
     }
-    n_own = (int)(sa - scell);                          // decoded by the rare path only
-    // immigrants: the walk goes on past the last staged plane (those stores land on a dump word),
-    // so the final position counts every disk, placed or not
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-        const float fc = F == 0 ? f4get(up.x03, up.x47, i) : f4get(up.y03, up.y47, i);
-        const float oc = F == 0 ? f4get(up.y03, up.y47, i) : f4get(up.x03, up.x47, i);
-        const float D = __fadd_rn(fc, -d);
-        const float Ds = __fadd_rn(D, sshift);                  // shiftCells.h:97
-        const bool imm = (i < up.cnt) & !((D > 0.0f) & (D <= w));              // shiftCells.h:94
-        if (imm) {
-            sts_pair(min(sa, sdump), F == 0 ? Ds : oc, F == 0 ? oc : Ds);      // sdump lies behind every slot of the tile
-            sa += step; step = PS - step;
-        }
-    }
-    const unsigned off = sa - scell;
-    return 2 * (int)(off / PS) + (step != 8u ? 1 : 0);
 }
+// walk offset (bytes from the cell's first chunk) -> number of disks walked over
+__device__ __forceinline__ int walk_count(unsigned off, unsigned PS) { return 2 * (int)(off / PS) + ((off & 8u) ? 1 : 0); }
 
 // a cell with 7 or 8 disks was produced (rare): stamp the flag word of its 2 x 2 block - and of
 // the blocks of its periodic images - so that the next sweep stages P3 for the tiles that see it;
@@ -391,97 +379,86 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     if (NS == 8) pown[3 * PLC] = make_float4(ox[6], ox[7], oy[6], oy[7]);
 }
 
-// ---- shiftCells(f, d) of this sweep for the owned cells and their way to HBM, in ONE pass (v11; v4-v10 had a
-// shift pass that left the tile in shared memory and a separate store pass).  One thread per destination cell:
-// V2 shiftCells.h:23-112 scatters the stayers of `own` and the immigrants from `up` into the cell's own staged
-// chunks in pair order (shift_into_tile), the same thread reads the three chunks back, turns them into
-// P0..P2 in registers (+ the in-band count and the "5 or more" flag, + the constant P3 of the fast path) and stores
-// them: no second pass over the tile, no second barrier, no count / flag round trip through shared memory.
-// Lanes run along x in both cases, so a warp stores runs of TX/2 consecutive float4 per parity.
-//   F = 1 (shift along y): thread = (segment of K rows, column); it walks its segment from the upstream end and
-//     keeps the raw cell u+1 in registers as `up` of cell u.  The raw cell beyond the segment belongs to another
-//     warp: it is read before the one CTA barrier of this pass.
-//   F = 0 (shift along x): warp = segment of K rows, lane = column; `up` is the neighbour lane's cell of the same
-//     row, so all hazards are inside the warp: __syncwarp() between the reads and the writes of a row, no
-//     CTA barrier at all.
+// ---- shiftCells(f, d) of this sweep for the owned cells and their way to HBM, in ONE pass (v11/v12; v4-v10
+// had a shift pass that left the tile in shared memory and a separate store pass).  One thread per destination
+// cell: the new content is scattered into the cell's own staged chunks in pair order (walk_scatter), the same
+// thread reads the chunks back, turns them into P0..P2 in registers (+ the in-band count, the "5 or more" flag,
+// the constant P3 of the fast path; slots beyond the new count are blanked in registers, nothing is pre-cleared)
+// and stores them.  No second pass over the tile, no count / flag round trip through shared memory.
+// Lanes run along x, permuted so that every quarter-warp touches 8 consecutive chunks of one column parity:
+// conflict-free LDS.128 / STS and 128-byte store segments.
+//   F = 0 (shift along x), PUSH: warp = K rows, lane = one cell of the row (tx owned + the extra upstream column).
+//     A lane keeps ONE cell in registers: it scatters its stayers into its own cell, gets the walk position of the
+//     cell downstream from that cell's lane by shuffle and appends its leavers there.  All hazards are inside the
+//     warp: __syncwarp() after the loads and before the read-back, no CTA barrier.
+//   F = 1 (shift along y), PULL: thread = (segment of K rows, column); it walks its segment from the upstream end
+//     and keeps the raw cell u+1 in registers as `up` of cell u.  The raw cell beyond the segment belongs to
+//     another warp: it is read before the one CTA barrier of this pass.
 template <int NS, typename TL, int NPL, int F>
 __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, const Geom4 &g, const SweepArgs &a,
                                                  float4 *__restrict__ dout, int sdir, float d, int tid, Counters *ctr)
 {
     constexpr int HB = TL::HB, PITCH = TL::PITCH, PLC = TL::PLC;
     constexpr unsigned PS = PLC * 16;
+    constexpr int NSL = 2 * NPL;                                    // slots that exist in shared memory
     const int TX = t.tx, TY = t.ty;
     const float w = g.w;
     const float sshift = sdir > 0 ? w : -w;                         // shiftCells.h:84-86
     const unsigned sdump = smem_u32(sm + (NPL - 1) * PLC + TL::PLB);    // padding behind the last staged plane
     const long long ps = (long long)2 * g.CH;                       // float4 chunks between planes
-    const long long rstride = 4 * ps;                               // ... between internal rows
 
-    auto cell_ptr = [&](int i, int j) -> float4 * {
+    auto cell_addr = [&](int i, int j) -> unsigned {
         const int is = i + t.xs;
-        return sm + j * PITCH + (is & 1) * HB + (is >> 1);
+        return smem_u32(sm + j * PITCH + (is & 1) * HB + (is >> 1));
     };
-    auto load_cell = [&](int i, int j, CellRegs &c) {               // P0..P3 -> plain x / y registers
-        const unsigned sp = smem_u32(cell_ptr(i, j));
+    auto load_cell = [&](unsigned sp, CellRegs &c) {                // P0..P3 -> plain x / y registers
         const float4 p0 = lds128<0>(sp), p1 = lds128<PS>(sp);
         c.x03 = p0; c.y03 = make_float4(p1.x, p1.y, p1.z, fabsf(p1.w));
+        c.x47 = make_float4(kSent, kSent, kSent, kSent);
+        c.y47 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NS >= 6) {                                              // higher slots: known to be unused in this tile
+            const float4 p2 = lds128<2 * PS>(sp);
+            c.x47.x = p2.x; c.x47.y = p2.y; c.y47.x = p2.z; c.y47.y = p2.w;
+        }
         if (NS == 8) {
-            const float4 p2 = lds128<2 * PS>(sp), p3 = lds128<(NPL == 4 ? 3 : 2) * PS>(sp);
-            c.x47 = make_float4(p2.x, p2.y, p3.x, p3.y); c.y47 = make_float4(p2.z, p2.w, p3.z, p3.w);
-            c.cnt = decode_cnt8(p3);
-        } else if (NS == 6) {               // the higher slots are known to be unused in this tile
-            const float4 p2 = lds128<2 * PS>(sp);
-            c.x47 = make_float4(p2.x, p2.y, kSent, kSent);
-            c.y47 = make_float4(p2.z, p2.w, 0.f, 0.f);
-            c.cnt = decode_cnt6(p2);
-        } else {
-            // NS = 4: no cell of the tile holds more than 4 disks; the count is in the bits of y5
-            const float4 p2 = lds128<2 * PS>(sp);
-            c.x47 = make_float4(kSent, kSent, kSent, kSent);
-            c.y47 = make_float4(0.f, 0.f, 0.f, 0.f);
-            c.cnt = __float_as_int(p2.w);
+            const float4 p3 = lds128<(NPL == 4 ? 3 : 2) * PS>(sp);
+            c.x47.z = p3.x; c.x47.w = p3.y; c.y47.z = p3.z; c.y47.w = p3.w;
         }
     };
-    // one destination cell: scatter, read back, store
-    auto emit = [&](int i, int j, const CellRegs &own, const CellRegs &up) {
-        const unsigned sp = smem_u32(cell_ptr(i, j));
-        const float4 empty2 = make_float4(kSent, 0.f, kSent, 0.f);  // two unused slots in pair order
-        sts128<0>(sp, empty2); sts128<PS>(sp, empty2); sts128<2 * PS>(sp, empty2);
-        if (NPL == 4) sts128<3 * PS>(sp, empty2);
-        int n_own;
-        int nNew = shift_into_tile<NS, F, NPL, PLC>(own, up, d, w, sshift, sp, sdump, n_own);
+    // the scattered cell -> HBM.  n_total = disks that want to be in the cell (more than NSL: rare path)
+    auto store_cell = [&](unsigned sp, int i, int j, int n_total, bool p3_done) {
         const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
         const int X = t.X0 + i, Y = t.Y0 + j;
-        bool p3_done = false;
-        if (nNew > 2 * NPL) {                           // rare: more disks than staged slots
-            int dropped;
-            if (NPL == 3) {
-                const int placed_own = 2 * (n_own / (int)PS) + ((n_own % (int)PS) ? 1 : 0);
-                dropped = shift_overflow3(F, up.x03, make_float2(up.x47.x, up.x47.y), up.y03,
-                                          make_float2(up.y47.x, up.y47.y), up.cnt, d, w, sshift, 2 * NPL - placed_own,
-                                          nNew, owned, dout, &g, &a, X, Y);
-                p3_done = true;                         // P3 of this cell is already in HBM
-            } else dropped = nNew - 2 * NPL;
-            nNew -= dropped;
-            if (dropped) {
+        int nNew = n_total;
+        if (n_total > NSL) {
+            const int cap = NPL == 3 ? (p3_done ? PMC_NMAX : NSL) : PMC_NMAX;
+            nNew = min(n_total, cap);
+            if (n_total > cap) {
                 atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
-                if (owned) atomicAdd(&ctr->lost, (unsigned long long)dropped);
+                if (owned) atomicAdd(&ctr->lost, (unsigned long long)(n_total - cap));
             }
         }
         if (NPL == 4 && nNew >= 7 && owned)
             crowded_cell_out(dout, a.flag_out, a.epoch_out, g.cps, g.rows, g.wrap_y, g.CH, g.FW, X, Y, 0,
                              make_float4(0.f, 0.f, 0.f, 0.f));
-        // pair order -> P0..P3, in-band counts and the "5 or more" flag (sign of y3)
+        // pair order -> P0..P3; slots beyond the count hold stale disks: blank them here
         const float4 c0 = lds128<0>(sp), c1 = lds128<PS>(sp), c2 = lds128<2 * PS>(sp);
-        const float4 q0 = make_float4(c0.x, c0.z, c1.x, c1.z);
-        const float4 q1 = make_float4(c0.y, c0.w, c1.y, nNew >= 5 ? -c1.w : c1.w);
-        const float4 q2 = make_float4(c2.x, c2.z, c2.y, nNew < 6 ? __int_as_float(nNew) : c2.w);
-        float4 q3 = make_float4(kSent, kSent, 0.f, __int_as_float(nNew));
+        float px[8] = { c0.x, c0.z, c1.x, c1.z, c2.x, c2.z, kSent, kSent };
+        float py[8] = { c0.y, c0.w, c1.y, c1.w, c2.y, c2.w, 0.f, 0.f };
         if (NPL == 4) {
             const float4 c3 = lds128<3 * PS>(sp);
-            q3 = make_float4(c3.x, c3.z, c3.y, nNew < PMC_NMAX ? __int_as_float(nNew) : c3.w);
+            px[6] = c3.x; px[7] = c3.z; py[6] = c3.y; py[7] = c3.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NSL; k++) {
+            const bool v = k < nNew;
+            px[k] = v ? px[k] : kSent; py[k] = v ? py[k] : 0.f;
         }
         if (!owned) return;
+        const float4 q0 = make_float4(px[0], px[1], px[2], px[3]);
+        const float4 q1 = make_float4(py[0], py[1], py[2], nNew >= 5 ? -py[3] : py[3]);     // "5 or more": sign of y3
+        const float4 q2 = make_float4(px[4], px[5], py[4], nNew < 6 ? __int_as_float(nNew) : py[5]);
+        const float4 q3 = make_float4(px[6], px[7], py[6], nNew < PMC_NMAX ? __int_as_float(nNew) : py[7]);
         float4 *dst = dout + ((long long)(Y * 4) * 2 + (X & 1)) * g.CH + (X >> 1);
         dst[0] = q0; dst[ps] = q1; dst[2 * ps] = q2;
         if (!p3_done) dst[3 * ps] = q3;
@@ -492,56 +469,93 @@ __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, c
 #pragma unroll 1
             for (int q = 1; q < 4; q++) {
                 if (((q & 1) && !ximg) || ((q & 2) && !yimg)) continue;
-                float4 *di = dst + ((q & 1) ? ximg : 0) + ((q & 2) ? (long long)yimg * rstride : 0);
+                float4 *di = dst + ((q & 1) ? ximg : 0) + ((q & 2) ? (long long)yimg * 4 * ps : 0);
                 di[0] = q0; di[ps] = q1; di[2 * ps] = q2;
                 if (!p3_done) di[3 * ps] = q3;
             }
         }
     };
+    // fast path, rare: more disks than staged slots.  The immigrants that did not fit go straight to the P3 chunk in HBM.
+    auto overflow3 = [&](const CellRegs &up, int n_stay, int n_total, int i, int j) {
+        int ucnt = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) ucnt += f4get(up.x03, up.x47, k) < kSentTest ? 1 : 0;
+        const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
+        shift_overflow3(F, up.x03, make_float2(up.x47.x, up.x47.y), up.y03, make_float2(up.y47.x, up.y47.y), ucnt,
+                        d, w, sshift, NSL - n_stay, n_total, owned, dout, &g, &a, t.X0 + i, t.Y0 + j);
+    };
 
     if (F == 1) {
-        // column strips: nseg = kNT / TX segments of K rows; (seg, col) by an exact multiply-shift (tid < 256)
-        const int seg = (tid * a.sh_inv) >> 16, col = tid - seg * TX;
+        // column strips: nseg = kNT / TX segments of K rows; (seg, c) by an exact multiply-shift (tid < 256);
+        // lanes take the even columns first, then the odd ones
+        const int seg = (tid * a.sh_inv) >> 16, c = tid - seg * TX, hx2 = TX >> 1;
+        const int col = c < hx2 ? 2 * c : 2 * (c - hx2) + 1;
         const int K = ((TY + a.sh_nseg - 1) * a.sh_inv2) >> 16, k0 = seg * K;      // ceil(TY / nseg)
         const int len = seg < a.sh_nseg ? min(K, TY - k0) : 0;
         const int i = t.ox0 + col;
         const int jb = t.oy0 + (sdir > 0 ? k0 : TY - 1 - k0);       // cell u of the strip = row jb + u * sdir
+        const int rs = sdir * PITCH * 16;                           // bytes from cell u to cell u + 1
+        unsigned sp = cell_addr(i, jb) + (len - 1) * rs;            // cell len - 1 (upstream end)
         CellRegs A, B;
         if (len > 0) {
-            load_cell(i, jb + (len - 1) * sdir, A);
-            load_cell(i, jb + len * sdir, B);
+            load_cell(sp, A);
+            load_cell(sp + rs, B);
         }
         __syncthreads();
+        auto emit = [&](int u, const CellRegs &own, const CellRegs &up) {
+            unsigned sa = sp, step = 8;
+            walk_scatter<NS, 1, true>(own, true, d, w, sshift, sa, step, PS, sdump);
+            const int n_stay = walk_count(sa - sp, PS);
+            walk_scatter<NS, 1, false>(up, true, d, w, sshift, sa, step, PS, sdump);
+            const int n_total = walk_count(sa - sp, PS);
+            bool p3_done = false;
+            if (NPL == 3 && n_total > NSL) { overflow3(up, n_stay, n_total, i, jb + u * sdir); p3_done = true; }
+            store_cell(sp, i, jb + u * sdir, n_total, p3_done);
+        };
         int u = len - 1;
 #pragma unroll 1
         for (int it = 0; it < 2; it++) {                // K <= 4: two ping-pong steps per iteration, no register copies
             if (u >= 0) {
-                emit(i, jb + u * sdir, A, B);
-                if (u > 0) load_cell(i, jb + (u - 1) * sdir, B);
+                emit(u, A, B);
+                sp -= rs;
+                if (u > 0) load_cell(sp, B);
             }
             u--;
             if (u >= 0) {
-                emit(i, jb + u * sdir, B, A);
-                if (u > 0) load_cell(i, jb + (u - 1) * sdir, A);
+                emit(u, B, A);
+                sp -= rs;
+                if (u > 0) load_cell(sp, A);
             }
             u--;
         }
     } else {
-        const int seg = tid >> 5, col = tid & 31;
+        // cell u of a row: u = 0 the most downstream owned column ... TX - 1, u = TX the extra upstream column.
+        // lane -> u: quarter-warps hold 8 cells of one parity (0 2 .. 14 | 1 3 .. 15 | 16 .. 30 | 17 .. 31)
+        const int lane = tid & 31, seg = tid >> 5;
+        const int u = ((lane >> 4) << 4) + ((lane & 7) << 1) + ((lane >> 3) & 1);
+        auto lane_of = [](int uu) { return ((uu >> 4) << 4) + ((uu & 1) << 3) + ((uu & 15) >> 1); };
+        const int lane_dn = lane_of(max(u - 1, 0)), lane_up = lane_of(min(u + 1, 31));
+        const bool act = u <= TX, dest = u < TX, push = act && u >= 1;
         const int K = (TY + kNT / 32 - 1) / (kNT / 32), k0 = seg * K;
         const int len = min(K, TY - k0);                // warp-uniform
-        const bool active = col < TX;
-        const int i = t.ox0 + col;
+        const int i = sdir > 0 ? t.ox0 + u : t.ox0 + TX - 1 - u;
+        unsigned sp = cell_addr(i, t.oy0 + k0), sp_dn = cell_addr(i - sdir, t.oy0 + k0);
 #pragma unroll 1
-        for (int v = 0; v < len; v++) {
+        for (int v = 0; v < len; v++, sp += PITCH * 16, sp_dn += PITCH * 16) {
             const int j = t.oy0 + k0 + v;
-            CellRegs A, B;
-            if (active) {
-                load_cell(i, j, A);
-                load_cell(i + sdir, j, B);
-            }
+            CellRegs c;
+            if (act) load_cell(sp, c);
             __syncwarp();
-            if (active) emit(i, j, A, B);
+            unsigned sa = sp, step = 8;
+            walk_scatter<NS, 0, true>(c, dest, d, w, sshift, sa, step, PS, sdump);
+            const unsigned off_dn = __shfl_sync(0xffffffffu, sa - sp, lane_dn);     // where the cell downstream stands
+            unsigned sb = sp_dn + off_dn, stepb = (off_dn & 8u) ? PS - 8 : 8;
+            walk_scatter<NS, 0, false>(c, push, d, w, sshift, sb, stepb, PS, sdump);
+            const int n_dn = walk_count(sb - sp_dn, PS);
+            if (NPL == 3 && push && n_dn > NSL) overflow3(c, walk_count(off_dn, PS), n_dn, i - sdir, j);
+            const int n_total = __shfl_sync(0xffffffffu, n_dn, lane_up);
+            __syncwarp();
+            if (dest) store_cell(sp, i, j, n_total, NPL == 3 && n_total > NSL);
         }
     }
 }
