@@ -174,26 +174,51 @@ __device__ __forceinline__ void sts_pair(unsigned saddr, float x, float y)
 // One source cell, one of the two roles.  STAY: its disks that remain (shiftCells.h:62: 0 < D <= w with D = c - d
 // along axis F) go to the walk position (sa, step) of their own cell.  !STAY: its disks that leave (shiftCells.h:94)
 // go, re-based by sshift (shiftCells.h:97), to the walk position of the cell downstream; that walk may run past
-// the last staged plane (7 or more disks want to be in the cell: rare), those stores land on a dump word behind
-// every slot of the tile, so that the final position still counts every disk.  `on` switches a lane off.
-// A slot is in use iff its x is not the sentinel (the unused y slots hold 0 or the in-band count).
+// the last staged plane (7 or more disks want to be in the cell: rare): nothing is stored at or beyond `lim`, but
+// the walk goes on, so that the final position counts every disk.  A slot is in use iff its x is below `thr`
+// (kSentTest; a lane is switched off with thr <= 0: cell-local coordinates are positive); a disk stays iff
+// 0 < D <= wl (a lane is switched off with wl <= 0).
+// One candidate = one straight-line block of predicated instructions (written in PTX: ptxas otherwise turns
+// every candidate into a branch with its own convergence barrier).
 template <int NS, int F, bool STAY>
-__device__ __forceinline__ void walk_scatter(const CellRegs &c, bool on, float d, float w, float sshift,
-                                             unsigned &sa, unsigned &step, unsigned PS, unsigned sdump)
+__device__ __forceinline__ void walk_scatter(const CellRegs &c, float d, float wl, float thr, float sshift,
+                                             unsigned &sa, unsigned &step, unsigned PS, unsigned lim)
 {
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         const float xi = f4get(c.x03, c.x47, i), yi = f4get(c.y03, c.y47, i);
-        const float D = __fadd_rn(F == 0 ? xi : yi, -d);
-        const bool inside = (D > 0.0f) & (D <= w);
-        // F = 0: an unused x slot holds the sentinel and is not `inside` on its own
-        const bool used = xi < kSentTest;
-        const bool p = on & (STAY ? ((F == 0 || used) & inside) : (used & !inside));
-        const float Dn = STAY ? D : __fadd_rn(D, sshift);
-        if (p) {
-            sts_pair(STAY ? sa : min(sa, sdump), F == 0 ? Dn : xi, F == 0 ? yi : Dn);
-            sa += step; step = PS - step;
+        const float fc = F == 0 ? xi : yi;
+        if (STAY) {
+            // D = fc - d (one rounding, == __fadd_rn(fc, -d)); p = 0 < D <= wl [and slot in use]; store (D, y) / (x, D)
+            if (F == 0)
+                asm volatile("{\n .reg .pred p;\n .reg .f32 D;\n"
+                             " sub.rn.f32 D, %2, %4;\n setp.gt.f32 p, D, 0f00000000;\n setp.le.and.f32 p, D, %5, p;\n"
+                             " @p st.shared.v2.f32 [%0], {D, %3};\n @p add.u32 %0, %0, %1;\n @p sub.u32 %1, %6, %1;\n}"
+                             : "+r"(sa), "+r"(step) : "f"(xi), "f"(yi), "f"(d), "f"(wl), "r"(PS) : "memory");
+            else
+                asm volatile("{\n .reg .pred p;\n .reg .f32 D;\n"
+                             " sub.rn.f32 D, %2, %4;\n setp.gt.f32 p, D, 0f00000000;\n setp.le.and.f32 p, D, %5, p;\n"
+                             " setp.lt.and.f32 p, %3, %7, p;\n"
+                             " @p st.shared.v2.f32 [%0], {%3, D};\n @p add.u32 %0, %0, %1;\n @p sub.u32 %1, %6, %1;\n}"
+                             : "+r"(sa), "+r"(step) : "f"(yi), "f"(xi), "f"(d), "f"(wl), "r"(PS), "f"(thr) : "memory");
+        } else {
+            // p = slot in use and not (0 < D <= wl); Ds = D + sshift; stored only below lim, walked in any case
+            if (F == 0)
+                asm volatile("{\n .reg .pred p, q;\n .reg .f32 D;\n"
+                             " sub.rn.f32 D, %2, %4;\n setp.gt.f32 q, D, 0f00000000;\n setp.le.and.f32 q, D, %5, q;\n"
+                             " setp.lt.and.f32 p, %2, %7, !q;\n add.rn.f32 D, D, %8;\n setp.lt.and.u32 q, %0, %9, p;\n"
+                             " @q st.shared.v2.f32 [%0], {D, %3};\n @p add.u32 %0, %0, %1;\n @p sub.u32 %1, %6, %1;\n}"
+                             : "+r"(sa), "+r"(step) : "f"(xi), "f"(yi), "f"(d), "f"(wl), "r"(PS), "f"(thr), "f"(sshift), "r"(lim)
+                             : "memory");
+            else
+                asm volatile("{\n .reg .pred p, q;\n .reg .f32 D;\n"
+                             " sub.rn.f32 D, %2, %4;\n setp.gt.f32 q, D, 0f00000000;\n setp.le.and.f32 q, D, %5, q;\n"
+                             " setp.lt.and.f32 p, %3, %7, !q;\n add.rn.f32 D, D, %8;\n setp.lt.and.u32 q, %0, %9, p;\n"
+                             " @q st.shared.v2.f32 [%0], {%3, D};\n @p add.u32 %0, %0, %1;\n @p sub.u32 %1, %6, %1;\n}"
+                             : "+r"(sa), "+r"(step) : "f"(yi), "f"(xi), "f"(d), "f"(wl), "r"(PS), "f"(thr), "f"(sshift), "r"(lim)
+                             : "memory");
         }
+        (void)fc;
     }
 }
 // walk offset (bytes from the cell's first chunk) -> number of disks walked over
@@ -404,12 +429,16 @@ __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, c
     const int TX = t.tx, TY = t.ty;
     const float w = g.w;
     const float sshift = sdir > 0 ? w : -w;                         // shiftCells.h:84-86
-    const unsigned sdump = smem_u32(sm + (NPL - 1) * PLC + TL::PLB);    // padding behind the last staged plane
-    const long long ps = (long long)2 * g.CH;                       // float4 chunks between planes
+    const unsigned ps = 2u * (unsigned)g.CH;                        // float4 chunks between planes (rows: 4 * ps)
 
     auto cell_addr = [&](int i, int j) -> unsigned {
         const int is = i + t.xs;
         return smem_u32(sm + j * PITCH + (is & 1) * HB + (is >> 1));
+    };
+    // chunk index of plane 0 of a region cell in the internal array (fits 32 bits: < 2^31 chunks at N = 2^28)
+    auto chunk_index = [&](int i, int j) -> unsigned {
+        const unsigned X = (unsigned)(t.X0 + i), Y = (unsigned)(t.Y0 + j);
+        return (Y * 8u + (X & 1u)) * (unsigned)g.CH + (X >> 1);
     };
     auto load_cell = [&](unsigned sp, CellRegs &c) {                // P0..P3 -> plain x / y registers
         const float4 p0 = lds128<0>(sp), p1 = lds128<PS>(sp);
@@ -425,51 +454,48 @@ __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, c
             c.x47.z = p3.x; c.x47.w = p3.y; c.y47.z = p3.z; c.y47.w = p3.w;
         }
     };
-    // the scattered cell -> HBM.  n_total = disks that want to be in the cell (more than NSL: rare path)
-    auto store_cell = [&](unsigned sp, int i, int j, int n_total, bool p3_done) {
-        const bool owned = (unsigned)(i - t.ox0) < (unsigned)t.nox && (unsigned)(j - t.oy0) < (unsigned)t.noy;
-        const int X = t.X0 + i, Y = t.Y0 + j;
+    auto clear_cell = [&](unsigned sp) {                            // two unused slots in pair order per chunk
+        const float4 empty2 = make_float4(kSent, 0.f, kSent, 0.f);
+        sts128<0>(sp, empty2); sts128<PS>(sp, empty2); sts128<2 * PS>(sp, empty2);
+        if (NPL == 4) sts128<3 * PS>(sp, empty2);
+    };
+    // the scattered cell -> HBM.  n_total = disks that want to be in the cell (more than NSL: rare path);
+    // gidx = chunk_index of the cell, (i, j) only for the rare paths
+    auto store_cell = [&](unsigned sp, unsigned gidx, bool owned, int i, int j, int n_total) {
         int nNew = n_total;
+        bool p3_done = false;
         if (n_total > NSL) {
-            const int cap = NPL == 3 ? (p3_done ? PMC_NMAX : NSL) : PMC_NMAX;
-            nNew = min(n_total, cap);
-            if (n_total > cap) {
+            p3_done = NPL == 3;                         // the pusher / puller wrote P3 of this cell to HBM
+            nNew = min(n_total, PMC_NMAX);
+            if (n_total > PMC_NMAX) {
                 atomicOr(&ctr->status, PMC_STATUS_OVERFLOW);
-                if (owned) atomicAdd(&ctr->lost, (unsigned long long)(n_total - cap));
+                if (owned) atomicAdd(&ctr->lost, (unsigned long long)(n_total - PMC_NMAX));
             }
         }
         if (NPL == 4 && nNew >= 7 && owned)
-            crowded_cell_out(dout, a.flag_out, a.epoch_out, g.cps, g.rows, g.wrap_y, g.CH, g.FW, X, Y, 0,
+            crowded_cell_out(dout, a.flag_out, a.epoch_out, g.cps, g.rows, g.wrap_y, g.CH, g.FW, t.X0 + i, t.Y0 + j, 0,
                              make_float4(0.f, 0.f, 0.f, 0.f));
-        // pair order -> P0..P3; slots beyond the count hold stale disks: blank them here
+        // pair order -> P0..P3, the in-band counts, the "5 or more" flag (sign of y3)
         const float4 c0 = lds128<0>(sp), c1 = lds128<PS>(sp), c2 = lds128<2 * PS>(sp);
-        float px[8] = { c0.x, c0.z, c1.x, c1.z, c2.x, c2.z, kSent, kSent };
-        float py[8] = { c0.y, c0.w, c1.y, c1.w, c2.y, c2.w, 0.f, 0.f };
+        const float4 q0 = make_float4(c0.x, c0.z, c1.x, c1.z);
+        const float4 q1 = make_float4(c0.y, c0.w, c1.y, nNew >= 5 ? -c1.w : c1.w);
+        const float4 q2 = make_float4(c2.x, c2.z, c2.y, nNew < 6 ? __int_as_float(nNew) : c2.w);
+        float4 q3 = make_float4(kSent, kSent, 0.f, __int_as_float(nNew));
         if (NPL == 4) {
             const float4 c3 = lds128<3 * PS>(sp);
-            px[6] = c3.x; px[7] = c3.z; py[6] = c3.y; py[7] = c3.w;
-        }
-#pragma unroll
-        for (int k = 0; k < NSL; k++) {
-            const bool v = k < nNew;
-            px[k] = v ? px[k] : kSent; py[k] = v ? py[k] : 0.f;
+            q3 = make_float4(c3.x, c3.z, c3.y, nNew < PMC_NMAX ? __int_as_float(nNew) : c3.w);
         }
         if (!owned) return;
-        const float4 q0 = make_float4(px[0], px[1], px[2], px[3]);
-        const float4 q1 = make_float4(py[0], py[1], py[2], nNew >= 5 ? -py[3] : py[3]);     // "5 or more": sign of y3
-        const float4 q2 = make_float4(px[4], px[5], py[4], nNew < 6 ? __int_as_float(nNew) : py[5]);
-        const float4 q3 = make_float4(px[6], px[7], py[6], nNew < PMC_NMAX ? __int_as_float(nNew) : py[7]);
-        float4 *dst = dout + ((long long)(Y * 4) * 2 + (X & 1)) * g.CH + (X >> 1);
-        dst[0] = q0; dst[ps] = q1; dst[2 * ps] = q2;
-        if (!p3_done) dst[3 * ps] = q3;
+        dout[gidx] = q0; dout[gidx + ps] = q1; dout[gidx + 2 * ps] = q2;
+        if (!p3_done) dout[gidx + 3 * ps] = q3;
         if (t.edge) {                                   // CTA-uniform: periodic images into the margins
-            const int ux = X - kMX, uy = Y - kMY, cps = g.cps;
+            const int ux = t.X0 + i - kMX, uy = t.Y0 + j - kMY, cps = g.cps;
             const int ximg = ux < kMX ? cps / 2 : (ux >= cps - kMX ? -(cps / 2) : 0);   // cps is even: parity is kept
             const int yimg = g.wrap_y ? (uy < kMY ? g.rows : (uy >= g.rows - kMY ? -g.rows : 0)) : 0;
 #pragma unroll 1
             for (int q = 1; q < 4; q++) {
                 if (((q & 1) && !ximg) || ((q & 2) && !yimg)) continue;
-                float4 *di = dst + ((q & 1) ? ximg : 0) + ((q & 2) ? (long long)yimg * 4 * ps : 0);
+                float4 *di = dout + gidx + ((q & 1) ? ximg : 0) + ((q & 2) ? (long long)yimg * 4 * ps : 0);
                 di[0] = q0; di[ps] = q1; di[2 * ps] = q2;
                 if (!p3_done) di[3 * ps] = q3;
             }
@@ -495,7 +521,10 @@ __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, c
         const int i = t.ox0 + col;
         const int jb = t.oy0 + (sdir > 0 ? k0 : TY - 1 - k0);       // cell u of the strip = row jb + u * sdir
         const int rs = sdir * PITCH * 16;                           // bytes from cell u to cell u + 1
+        const bool xown = (unsigned)col < (unsigned)t.nox;
         unsigned sp = cell_addr(i, jb) + (len - 1) * rs;            // cell len - 1 (upstream end)
+        unsigned gidx = chunk_index(i, jb + (len - 1) * sdir);
+        const unsigned grs = (unsigned)(sdir * 4) * ps;             // chunks from cell u to cell u + 1
         CellRegs A, B;
         if (len > 0) {
             load_cell(sp, A);
@@ -503,27 +532,28 @@ __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, c
         }
         __syncthreads();
         auto emit = [&](int u, const CellRegs &own, const CellRegs &up) {
+            const int j = jb + u * sdir;
+            clear_cell(sp);
             unsigned sa = sp, step = 8;
-            walk_scatter<NS, 1, true>(own, true, d, w, sshift, sa, step, PS, sdump);
+            walk_scatter<NS, 1, true>(own, d, w, kSentTest, sshift, sa, step, PS, 0u);
             const int n_stay = walk_count(sa - sp, PS);
-            walk_scatter<NS, 1, false>(up, true, d, w, sshift, sa, step, PS, sdump);
+            walk_scatter<NS, 1, false>(up, d, w, kSentTest, sshift, sa, step, PS, sp + NPL * PS);
             const int n_total = walk_count(sa - sp, PS);
-            bool p3_done = false;
-            if (NPL == 3 && n_total > NSL) { overflow3(up, n_stay, n_total, i, jb + u * sdir); p3_done = true; }
-            store_cell(sp, i, jb + u * sdir, n_total, p3_done);
+            if (NPL == 3 && n_total > NSL) overflow3(up, n_stay, n_total, i, j);
+            store_cell(sp, gidx, xown && (unsigned)(j - t.oy0) < (unsigned)t.noy, i, j, n_total);
         };
         int u = len - 1;
 #pragma unroll 1
         for (int it = 0; it < 2; it++) {                // K <= 4: two ping-pong steps per iteration, no register copies
             if (u >= 0) {
                 emit(u, A, B);
-                sp -= rs;
+                sp -= rs; gidx -= grs;
                 if (u > 0) load_cell(sp, B);
             }
             u--;
             if (u >= 0) {
                 emit(u, B, A);
-                sp -= rs;
+                sp -= rs; gidx -= grs;
                 if (u > 0) load_cell(sp, A);
             }
             u--;
@@ -539,23 +569,28 @@ __device__ __forceinline__ void shift_store_pass(float4 *sm, const TileCtx &t, c
         const int K = (TY + kNT / 32 - 1) / (kNT / 32), k0 = seg * K;
         const int len = min(K, TY - k0);                // warp-uniform
         const int i = sdir > 0 ? t.ox0 + u : t.ox0 + TX - 1 - u;
+        const bool xown = dest && (unsigned)(i - t.ox0) < (unsigned)t.nox;
+        const float w_stay = dest ? w : -1.0f, thr_push = push ? kSentTest : -1.0f;    // lane switches of walk_scatter
         unsigned sp = cell_addr(i, t.oy0 + k0), sp_dn = cell_addr(i - sdir, t.oy0 + k0);
+        unsigned gidx = chunk_index(i, t.oy0 + k0);
 #pragma unroll 1
-        for (int v = 0; v < len; v++, sp += PITCH * 16, sp_dn += PITCH * 16) {
+        for (int v = 0; v < len; v++, sp += PITCH * 16, sp_dn += PITCH * 16, gidx += 4 * ps) {
             const int j = t.oy0 + k0 + v;
             CellRegs c;
             if (act) load_cell(sp, c);
             __syncwarp();
+            if (dest) clear_cell(sp);
             unsigned sa = sp, step = 8;
-            walk_scatter<NS, 0, true>(c, dest, d, w, sshift, sa, step, PS, sdump);
+            walk_scatter<NS, 0, true>(c, d, w_stay, kSentTest, sshift, sa, step, PS, 0u);
+            __syncwarp();                               // the cleared chunks before the neighbour lane's leavers
             const unsigned off_dn = __shfl_sync(0xffffffffu, sa - sp, lane_dn);     // where the cell downstream stands
             unsigned sb = sp_dn + off_dn, stepb = (off_dn & 8u) ? PS - 8 : 8;
-            walk_scatter<NS, 0, false>(c, push, d, w, sshift, sb, stepb, PS, sdump);
+            walk_scatter<NS, 0, false>(c, d, w, thr_push, sshift, sb, stepb, PS, sp_dn + NPL * PS);
             const int n_dn = walk_count(sb - sp_dn, PS);
             if (NPL == 3 && push && n_dn > NSL) overflow3(c, walk_count(off_dn, PS), n_dn, i - sdir, j);
             const int n_total = __shfl_sync(0xffffffffu, n_dn, lane_up);
             __syncwarp();
-            if (dest) store_cell(sp, i, j, n_total, NPL == 3 && n_total > NSL);
+            if (dest) store_cell(sp, gidx, xown && (unsigned)(j - t.oy0) < (unsigned)t.noy, i, j, n_total);
         }
     }
 }
