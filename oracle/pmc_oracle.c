@@ -270,36 +270,45 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
     int cnt = n[cell];
     if (cnt == 0) return;                                 /* subsweep.h:252-254 */
     float *X = disk + cell * 2 * nm, *Y = X + nm;         /* cpy_to_Dsh subsweep.h:18-27 */
-    /* all random words of this cell's sub-sweep: one Philox call feeds two trials */
+    /* all random words of this cell's sub-sweep.  Uniform proposal: ONE 32-bit word per trial
+     * (dx: bits 20-31, dy: bits 8-19, shuffle: bits 0-7), one Philox call feeds four trials.
+     * Gaussian proposal: two words per trial (23 + 1 bits per axis), one call feeds two trials. */
     uint32_t words[2 * 64 + 4];
-    for (int c = 0; c < (g->n_M + 1) / 2; c++)
+    const int per_call = g->proposal == 1 ? 2 : 4;
+    for (int c = 0; c < (g->n_M + per_call - 1) / per_call; c++)
         trial_rng(g, (uint32_t)cell, sweep, (uint32_t)c, words + 4 * c);
     /* random_shuffle subsweep.h:50-58 as intended: a physical Fisher-Yates shuffle of the
      * cell's slots, written back with the cell like the reference's D_sh.  Only the first
      * min(n_M, cnt) positions are ever visited by the trial loop, so the shuffle stops there
-     * (partial Fisher-Yates: positions 0..k-1 hold a uniform ordered sample).  Step s takes
-     * its 16 random bits from the low bytes of trial s's two words. */
+     * (partial Fisher-Yates: positions 0..k-1 hold an ordered sample without replacement).  Step s
+     * takes its random bits from the low byte(s) of trial s's word(s): 8 bits (uniform proposal: the
+     * choice among m <= 8 remaining slots is uniform to 1 part in 256 / m) or 16 bits (Gaussian).
+     * Which disk a trial moves never depends on the positions, so detailed balance is not affected. */
     int steps = g->n_M < cnt ? g->n_M : cnt;
     for (int s = 0; s < steps; s++) {
-        uint32_t ra = words[2 * s], rb = words[2 * s + 1];
-        uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
-        int j = s + (int)((b16 * (uint32_t)(cnt - s)) >> 16);
+        int j;
+        if (g->proposal == 1) {
+            uint32_t ra = words[2 * s], rb = words[2 * s + 1];
+            uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
+            j = s + (int)((b16 * (uint32_t)(cnt - s)) >> 16);
+        } else {
+            j = s + (int)(((words[s] & 0xFFu) * (uint32_t)(cnt - s)) >> 8);
+        }
         float t;
         t = X[s]; X[s] = X[j]; X[j] = t;
         t = Y[s]; Y[s] = Y[j]; Y[j] = t;
     }
     const uint32_t nM2 = 2u * (uint32_t)g->M + 1u;
     for (int s = 0; s < g->n_M; s++) {                    /* subsweep.h:279 */
-        uint32_t ra = words[2 * s], rb = words[2 * s + 1];
+        uint32_t ra = g->proposal == 1 ? words[2 * s] : words[s], rb = g->proposal == 1 ? words[2 * s + 1] : 0u;
         int slot = s % cnt;                               /* i = (i+1) mod atom_counts, subsweep.h:291-296 */
         /* make_move subsweep.h:60-71; proposal = uniform in the square on
-         * the coordinate grid: m * q per axis with m = floor((2 r24 + 1) * (2M+1) / 2^25) - M from
-         * the top 24 bits r24 of the word.  P(m) == P(-m) exactly: r24 -> 2^24 - 1 - r24 maps the
-         * odd number 2 r24 + 1 to 2^25 - (2 r24 + 1), and odd * odd / 2^25 is never an integer, so
-         * the floor maps m to -m.  A symmetric proposal is all detailed balance needs.  (The low 8
-         * bits of the words feed the shuffle above.)  x + m*q is exact. */
-        int mx = (int)((((uint64_t)(ra >> 8) * 2u + 1u) * nM2) >> 25) - g->M;
-        int my = (int)((((uint64_t)(rb >> 8) * 2u + 1u) * nM2) >> 25) - g->M;
+         * the coordinate grid: m * q per axis with m = floor((2 r12 + 1) * (2M+1) / 2^13) - M from
+         * a 12-bit field r12 of the word.  P(m) == P(-m) exactly: r12 -> 2^12 - 1 - r12 maps the
+         * odd number 2 r12 + 1 to 2^13 - (2 r12 + 1), and odd * odd / 2^13 is never an integer, so
+         * the floor maps m to -m.  A symmetric proposal is all detailed balance needs.  x + m*q is exact. */
+        int mx = (int)((((uint64_t)(ra >> 20) * 2u + 1u) * nM2) >> 13) - g->M;
+        int my = (int)((((uint64_t)((ra >> 8) & 0xFFFu) * 2u + 1u) * nM2) >> 13) - g->M;
         if (g->proposal == 1) {
             /* the reference's proposal, make_move subsweep.h:60-71: x + curand_normal * sigma per axis.
              * Box-Muller on bits 8..30 of the two words (radius from ra, angle in the first quadrant from

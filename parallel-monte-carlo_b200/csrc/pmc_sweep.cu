@@ -416,15 +416,18 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                 const float4 x03 = pown[0], x47 = pown[PL], y03 = pown[2 * PL], y47 = pown[3 * PL];
                 float ox[8] = { x03.x, x03.y, x03.z, x03.w, x47.x, x47.y, x47.z, x47.w };
                 float oy[8] = { y03.x, y03.y, y03.z, y03.w, y47.x, y47.y, y47.z, y47.w };
+                // uniform proposal: one word per trial (one Philox call); Gaussian: two words per trial (two calls)
+                const bool gauss = g.proposal == PMC_PROPOSAL_GAUSSIAN;
                 uint32_t rw[8];
                 philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.seed_lo, g.seed_hi, rw[0], rw[1], rw[2], rw[3]);
-                philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.seed_lo, g.seed_hi, rw[4], rw[5], rw[6], rw[7]);
+                if (gauss) philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.seed_lo, g.seed_hi, rw[4], rw[5], rw[6], rw[7]);
                 // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     const uint32_t b16 = ((rw[2 * s] & 0xFFu) << 8) | (rw[2 * s + 1] & 0xFFu);
                     const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
-                    const int jj = s + (int)((b16 * (uint32_t)mrem) >> 16);
+                    const int jj = s + (gauss ? (int)((b16 * (uint32_t)mrem) >> 16)
+                                              : (int)(((rw[s] & 0xFFu) * (uint32_t)mrem) >> 8));
                     const float tx = ox[s], ty = oy[s];
                     float nx = tx, ny = ty;
 #pragma unroll
@@ -443,8 +446,8 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
                     const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
                     const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-                    float mx = grid_disp(rw[2 * s], g.nM2, g.mofs), my = grid_disp(rw[2 * s + 1], g.nM2, g.mofs);
-                    if (g.proposal == PMC_PROPOSAL_GAUSSIAN) gauss_disp(rw[2 * s], rw[2 * s + 1], g.M, mx, my);
+                    float mx = grid_disp_hi(rw[s], g.nM2, g.mofs), my = grid_disp_lo(rw[s], g.nM2, g.mofs);
+                    if (gauss) gauss_disp(rw[2 * s], rw[2 * s + 1], g.M, mx, my);
                     const float px = __fmaf_rn(mx, dscale, x);     // make_move subsweep.h:60-71
                     const float py = __fmaf_rn(my, dscale, y);
                     my_trials += owned ? 1u : 0u;
@@ -485,15 +488,20 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                 auto slot_ptr = [&](int slot) { return fown + (slot >> 2) * (PL * 4) + (slot & 3); };
                 const int steps = n_M < cnt ? n_M : cnt;
 #pragma unroll 1
-                for (int s0 = 0; s0 < steps; s0 += 2) {     // shuffle first (needs every call's low bytes)
-                    uint32_t r0, r1, r2, r3;
-                    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, (uint32_t)(s0 >> 1), g.seed_lo, g.seed_hi, r0, r1, r2, r3);
+                const bool gauss = g.proposal == PMC_PROPOSAL_GAUSSIAN;
+                const int per_call = gauss ? 2 : 4;         // trials fed by one Philox call (oracle subsweep_cell)
 #pragma unroll 1
-                    for (int h = 0; h < 2 && s0 + h < steps; h++) {
+                for (int s0 = 0; s0 < steps; s0 += per_call) {     // shuffle first (needs every call's low bytes)
+                    uint32_t r[4];
+                    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, (uint32_t)(s0 / per_call), g.seed_lo, g.seed_hi, r[0], r[1], r[2], r[3]);
+#pragma unroll 1
+                    for (int h = 0; h < per_call && s0 + h < steps; h++) {
                         const int s = s0 + h;
-                        const uint32_t ra = h ? r2 : r0, rb = h ? r3 : r1;
+                        const uint32_t ra = gauss ? (h ? r[2] : r[0]) : (h == 0 ? r[0] : h == 1 ? r[1] : h == 2 ? r[2] : r[3]);
+                        const uint32_t rb = h ? r[3] : r[1];
                         const uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
-                        const int jj = s + (int)((b16 * (uint32_t)(cnt - s)) >> 16);
+                        const int jj = s + (gauss ? (int)((b16 * (uint32_t)(cnt - s)) >> 16)
+                                                  : (int)(((ra & 0xFFu) * (uint32_t)(cnt - s)) >> 8));
                         float *ps = slot_ptr(s), *pj = slot_ptr(jj);
                         const float xs = ps[0], ys = ps[2 * PL * 4], xj = pj[0], yj = pj[2 * PL * 4];
                         ps[0] = xj; ps[2 * PL * 4] = yj; pj[0] = xs; pj[2 * PL * 4] = ys;
@@ -503,13 +511,15 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
 #pragma unroll 1
                 for (int s = 0; s < n_M; s++) {             // subsweep.h:279
                     uint32_t r0, r1, r2, r3;
-                    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, (uint32_t)(s >> 1), g.seed_lo, g.seed_hi, r0, r1, r2, r3);
-                    const uint32_t ra = (s & 1) ? r2 : r0, rb = (s & 1) ? r3 : r1;
+                    philox4x32_10(cell_id, a.sweep_lo, a.sweep_hi, (uint32_t)(s / per_call), g.seed_lo, g.seed_hi, r0, r1, r2, r3);
+                    const int h = s % per_call;
+                    const uint32_t ra = gauss ? (h ? r2 : r0) : (h == 0 ? r0 : h == 1 ? r1 : h == 2 ? r2 : r3);
+                    const uint32_t rb = h ? r3 : r1;
                     float *fx = slot_ptr(it), *fy = fx + 2 * PL * 4;
                     it = (it + 1 >= cnt) ? 0 : it + 1;
                     const float x = *fx, y = *fy;
-                    float mx = grid_disp(ra, g.nM2, g.mofs), my = grid_disp(rb, g.nM2, g.mofs);
-                    if (g.proposal == PMC_PROPOSAL_GAUSSIAN) gauss_disp(ra, rb, g.M, mx, my);
+                    float mx = grid_disp_hi(ra, g.nM2, g.mofs), my = grid_disp_lo(ra, g.nM2, g.mofs);
+                    if (gauss) gauss_disp(ra, rb, g.M, mx, my);
                     const float px = __fmaf_rn(mx, dscale, x);
                     const float py = __fmaf_rn(my, dscale, y);
                     my_trials += owned ? 1u : 0u;

@@ -335,15 +335,14 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
 
     float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
     float oy[8] = { p1.x, p1.y, p1.z, fabsf(p1.w), p2.z, p2.w, p3.z, p3.w };     // y3 carries the "5 or more" flag in its sign
-    uint32_t rw[8];
+    // ONE Philox call per cell and sub-sweep: word s feeds trial s (dx: bits 20-31, dy: bits 8-19, shuffle: bits 0-7)
+    uint32_t rw[4];
     philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.pk0, g.pk1, rw[0], rw[1], rw[2], rw[3]);
-    philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 1u, g.pk0, g.pk1, rw[4], rw[5], rw[6], rw[7]);
     // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-        const uint32_t b16 = ((rw[2 * s] & 0xFFu) << 8) | (rw[2 * s + 1] & 0xFFu);
         const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
-        const int jj = s + (int)((b16 * (uint32_t)mrem) >> 16);
+        const int jj = s + (int)(((rw[s] & 0xFFu) * (uint32_t)mrem) >> 8);
         const float tx = ox[s], ty = oy[s];
         float nx = tx, ny = ty;
 #pragma unroll
@@ -362,8 +361,8 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
         const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
         const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-        const float px = __fmaf_rn(grid_disp(rw[2 * s], g.nM2, g.mofs), dscale, x);     // make_move subsweep.h:60-71
-        const float py = __fmaf_rn(grid_disp(rw[2 * s + 1], g.nM2, g.mofs), dscale, y);
+        const float px = __fmaf_rn(grid_disp_hi(rw[s], g.nM2, g.mofs), dscale, x);      // make_move subsweep.h:60-71
+        const float py = __fmaf_rn(grid_disp_lo(rw[s], g.nM2, g.mofs), dscale, y);
         bool inb;
         float m = neighbours_min_d2(px, py, inb);
         // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
