@@ -231,7 +231,8 @@ class ParallelMC:
         _ck(lib().pmc_synchronize(self._h))
 
     def set_tuning(self, name, value):
-        """Result-invariant knobs (pmc_set_tuning): bands, prefetch, overlap, generic, force_crowded, no_ns4, full_halo."""
+        """Result-invariant knobs (pmc_set_tuning): bands, prefetch, overlap, generic, four_plane, force_crowded, no_ns4,
+        full_halo, tile_rows."""
         _ck(lib().pmc_set_tuning(self._h, name.encode(), int(value)))
 
     def alloc_r(self):

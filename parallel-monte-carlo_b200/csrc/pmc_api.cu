@@ -103,7 +103,7 @@ struct pmc_handle {
     unsigned v4_epoch[2], v4_epoch_next;
     long long launches;         // kernels launched by this handle since the last pmc_reset_counters
     // result-invariant tuning knobs (pmc_set_tuning)
-    int tune_bands, tune_prefetch, tune_overlap, tune_generic, tune_force, tune_four_plane;
+    int tune_bands, tune_prefetch, tune_overlap, tune_generic, tune_force, tune_four_plane, tune_tile_rows;
     unsigned status_sticky;     // status bits already handed to the caller as a return code (pmc_get_counters ORs them back in)
     Counters *h_ctr;            // pinned host mirror for the status read of blocking calls
     alignas(64) unsigned char v4_tmap[2][2][128];   // [buffer][0: full-tile box, 1: half-height box]
@@ -334,6 +334,7 @@ int pmc_destroy(pmc_handle *h)
 //   "overlap" (0/1)       slab runs: boundary rows + NCCL ring on a side stream (default 1)
 //   "generic" (0/1)       use the generic fused kernel (pmc_sweep.cu) even where the fast path qualifies
 //   "four_plane" (0/1)    fast path with all four planes staged and no crowded-cell flag lookup (3 CTAs / SM)
+//   "tile_rows" (0, 2..28 even)   cap on the owned rows of a tile (0 = automatic: 16 for systems of less than ~1.5 waves)
 //   "force_crowded", "no_ns4", "full_halo" (0/1)   drive the rare paths of the fast kernel on ordinary tiles
 int pmc_set_tuning(pmc_handle *h, const char *name, int value)
 {
@@ -344,6 +345,7 @@ int pmc_set_tuning(pmc_handle *h, const char *name, int value)
     if (!strcmp(name, "overlap")) { h->tune_overlap = value ? 1 : 0; return 0; }
     if (!strcmp(name, "generic")) { h->tune_generic = value ? 1 : 0; return 0; }
     if (!strcmp(name, "four_plane")) { h->tune_four_plane = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "tile_rows")) { if (value < 0 || value > 28 || (value & 1)) return PMC_E_INVALID; h->tune_tile_rows = value; return 0; }
     if (!strcmp(name, "force_crowded")) return flag(8);
     if (!strcmp(name, "no_ns4")) return flag(16);
     if (!strcmp(name, "full_halo")) return flag(64);
@@ -609,6 +611,11 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         }
     }
     const int pf_ahead = h->tune_prefetch;
+    // tile height: what the colour order allows (24..28 rows) unless the whole system is less than ~1.5 waves of such
+    // tiles (148 SMs x 4 CTAs): then 16-row tiles, whose shorter CTAs shorten the dependency chain from sweep to sweep
+    // (N = 2^20: 28.9 -> 25.9 us per sweep; larger systems lose throughput to the deeper halo).  "tile_rows" overrides.
+    int ty_cap = h->tune_tile_rows;
+    if (!ty_cap && (long long)((h->g4.cps + 27) / 28) * ((h->g4.rows + 25) / 26) < 888) ty_cap = 16;
     // the event pair that times the sweep kernels of this call; owned by this scope until it is queued
     struct EvPair {
         cudaEvent_t a = nullptr, b = nullptr;
@@ -664,6 +671,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         a.dbg_skip = dbg;
         a.prefetch_ahead = pf_ahead;
         pmc4_plan_sweep(a, dbg & 64);               // tile extent and halo from the colour order (64: always the full halo)
+        if (ty_cap && a.ty > ty_cap) a.ty = ty_cap; // small systems: shorter tiles, more CTAs per sweep
         h->v4_epoch[cur ^ 1] = next_epoch();
         a.flag_in = h->v4_flags[cur]; a.epoch_in = h->v4_epoch[cur];
         a.flag_out = h->v4_flags[cur ^ 1]; a.epoch_out = h->v4_epoch[cur ^ 1];

@@ -171,14 +171,14 @@ __device__ __forceinline__ void philox4x32_10_keys(uint32_t c0, uint32_t c1, uin
 // Trial displacement in grid units (make_move subsweep.h:60-71, proposal uniform in the square on
 // the coordinate grid): m = floor((2 r12 + 1) * (2M+1) / 2^13) - M from a 12-bit field r12 of the trial's
 // random word (exactly symmetric, P(m) == P(-m)), as an exact float and without I2F: with the field
-// in the top 12 bits, (r & 0xFFF00000) | 0x80000 = 2^19 (2 r12 + 1), and the high half of the product
-// with 2M+1 leaves 2^23 + floor(..) in the mantissa of a float.  _hi: bits 20-31 (x), _lo: bits 8-19 (y).
+// in the top 12 bits, (r & 0xFFF00000) | 0x80000 = 2^19 (2 r12 + 1), the high half of the product with
+// 2M+1 is floor(..), and OR-ed into the mantissa of 2^23 it is a float.  _hi: bits 20-31 (x), _lo: bits 8-19 (y).
 // Identical to oracle/pmc_oracle.c subsweep_cell.
 __device__ __forceinline__ float grid_disp_hi(uint32_t r, unsigned nM2, float mofs)
 {
-    uint32_t tb;
-    asm("mad.hi.u32 %0, %1, %2, 1258291200;" : "=r"(tb) : "r"((r & 0xFFF00000u) | 0x80000u), "r"(nM2));   // + 0x4B000000
-    return __fadd_rn(__uint_as_float(tb), -mofs);
+    // t <= 2M < 2^23 (pmc_create: M < 2^22): OR-ing it into the mantissa of 2^23 is the exact float 2^23 + t
+    const uint32_t t = __umulhi((r & 0xFFF00000u) | 0x80000u, nM2);
+    return __fadd_rn(__uint_as_float(t | 0x4B000000u), -mofs);
 }
 __device__ __forceinline__ float grid_disp_lo(uint32_t r, unsigned nM2, float mofs)
 {

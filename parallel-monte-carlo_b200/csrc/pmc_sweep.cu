@@ -487,7 +487,6 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                 float *fown = reinterpret_cast<float *>(pown);
                 auto slot_ptr = [&](int slot) { return fown + (slot >> 2) * (PL * 4) + (slot & 3); };
                 const int steps = n_M < cnt ? n_M : cnt;
-#pragma unroll 1
                 const bool gauss = g.proposal == PMC_PROPOSAL_GAUSSIAN;
                 const int per_call = gauss ? 2 : 4;         // trials fed by one Philox call (oracle subsweep_cell)
 #pragma unroll 1

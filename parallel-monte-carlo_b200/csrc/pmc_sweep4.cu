@@ -164,13 +164,8 @@ __device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float np
 // V2 shiftCells.h:23-112.  The new content of a destination cell - the stayers of the cell itself in slot
 // order, then the immigrants from the cell upstream in slot order - is scattered into the cell's own staged
 // chunks in PAIR order: chunk c (plane c) = (x_2c, y_2c, x_2c+1, y_2c+1), so that one 8-byte store places a
-// disk and the slot -> address walk is two adds (+8, then +plane stride - 8, alternating); the way out to HBM
+// disk (st.shared.v2.f32) and the slot -> address walk is two adds (+8, then +plane stride - 8, alternating); the way out to HBM
 // converts to P0..P3 in registers.
-__device__ __forceinline__ void sts_pair(unsigned saddr, float x, float y)
-{
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(x), "f"(y) : "memory");
-}
-
 // One source cell, one of the two roles.  STAY: its disks that remain (shiftCells.h:62: 0 < D <= w with D = c - d
 // along axis F) go to the walk position (sa, step) of their own cell.  !STAY: its disks that leave (shiftCells.h:94)
 // go, re-based by sshift (shiftCells.h:97), to the walk position of the cell downstream; that walk may run past

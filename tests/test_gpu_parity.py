@@ -485,7 +485,8 @@ def test_crowded_cells_use_the_eight_slot_path_and_match_the_oracle():
     assert c["lost"] > 0 and c["status"] & 1
 
 
-@pytest.mark.parametrize("knob", ["force_crowded", "no_ns4", "full_halo", "generic", "four_plane", "bands1"])
+@pytest.mark.parametrize("knob", ["force_crowded", "no_ns4", "full_halo", "generic", "four_plane", "bands1", "tile_rows8",
+                                  "tile_rows28"])
 def test_tuning_knobs_never_change_the_result(knob):
     """pmc_set_tuning chooses which kernel / schedule computes the sweep, never the result: "force_crowded"
     sends EVERY tile down the crowded-tile path (half-height pieces with all four planes staged), "full_halo"
@@ -495,6 +496,8 @@ def test_tuning_knobs_never_change_the_result(knob):
     mc, o = pair(N)
     if knob == "bands1":
         mc.set_tuning("bands", 1)
+    elif knob.startswith("tile_rows"):
+        mc.set_tuning("tile_rows", int(knob[9:]))     # N = 2^16 runs with 16-row tiles by default (small system)
     else:
         mc.set_tuning(knob, 1)
     disk, n = mc.assign(mc.init_r())
