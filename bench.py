@@ -185,10 +185,32 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: everything else that a library writes to file descriptor 1
+    (NCCL prints its version banner there when NCCL_DEBUG is set) is sent to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -198,8 +220,8 @@ def main():
     ap.add_argument("--sweeps-per-step", type=int, default=1000,
                     help="MC sweeps per step; default = the reference's MCpasses (start.cu:24)")
     ap.add_argument("--burn-in", type=int, default=300)
-    ap.add_argument("--ref-sweeps", type=int, default=2, help="sweeps per step of the CPU arm")
-    ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the cpu_baseline sample")
+    ap.add_argument("--ref-sweeps", type=int, default=20, help="sweeps per step of the CPU arm")
+    ap.add_argument("--cpu-sweeps", type=int, default=60, help="sweeps of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -428,7 +450,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(gpu_launches),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
