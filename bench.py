@@ -56,6 +56,26 @@ def default_workload(world_env):
     return "n256m_phi0.70" if world_env else "n16m_phi0.70"
 
 
+def bind_to_gpu_numa(torch, device):
+    """Slab runs copy 0.6 GB per rank and step each way: pin this process (and therefore the first-touch placement
+    of its pinned buffers) to the CPUs of the NUMA node the GPU hangs off.  Returns what was done (for the JSON)."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpulist = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no local cpus in the affinity mask"
+        os.sched_setaffinity(0, cpus)
+        return f"{bdf}: {len(cpus)} local cpus"
+    except Exception as e:                      # sysfs not exposed (containers): leave the mask alone
+        return f"unchanged ({type(e).__name__})"
+
+
 def state_hash(torch, disk, n, g, dist):
     """64-bit hash of the owned cells (position bits and counts), a wrapping SUM over cells of a mix of
     (global cell id, the cell's 16 words, its count): independent of how cells are spread over ranks, so
@@ -251,6 +271,7 @@ def main():
         dist.barrier()
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     n_ranks = world
+    numa = bind_to_gpu_numa(torch, local_rank) if n_ranks > 1 else None
 
     workload = args.workload or default_workload("WORLD_SIZE" in os.environ or n_ranks > 1)
     N, phi, mult, delta = WORKLOADS[workload]
@@ -383,16 +404,47 @@ def main():
                "what": "pmc_run_host: H2D(r) + assign + sweeps + D2H(disk, n), pinned host buffers",
                "n_sum_check": int(n_host.to(torch.int64).sum().item())}
     elif not args.no_e2e:
-        # slab runs: every rank's slab (caller layout, ghost rows included) starts and ends each step in
-        # pinned host memory; pmc_sweep runs on the device copy in between (ghost rows exchanged by NCCL)
-        disk_host = disk.cpu().pin_memory()
-        n_host = n.cpu().pin_memory()
-        mc.set_blocking(1)
-        for _ in range(2):
-            disk.copy_(disk_host, non_blocking=True); n.copy_(n_host, non_blocking=True)
-            mc.sweep(disk, n, sweep, S)
-            disk_host.copy_(disk, non_blocking=True); n_host.copy_(n, non_blocking=True)
-            sweep += S
+        # slab runs: a stream of independent jobs, like the single-GPU leg (every step starts from the same host
+        # input).  Per step and rank: H2D(slab disk, n) from pinned memory + pmc_sweep (S sweeps, NCCL ghost rows)
+        # + D2H(slab disk, n) into pinned memory.  Two device copies of the slab: the H2D of step i + 1 and the
+        # D2H of step i - 1 run on copy streams while step i sweeps.  (Inside ONE step nothing can overlap: a band
+        # of rows can run sweep t only when its neighbours have done sweep t - 1, so while the copy is in flight at
+        # most ~bands/2 of the 1000 sweeps could start.)
+        disk_in = disk.cpu().pin_memory()
+        n_in = n.cpu().pin_memory()
+        dbuf = [(disk, n), (torch.empty_like(disk), torch.empty_like(n))]
+        hout = [(torch.empty_like(disk_in).pin_memory(), torch.empty_like(n_in).pin_memory()) for _ in range(2)]
+        main_s = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_swept = [torch.cuda.Event() for _ in range(2)]
+        ev_d2h = [torch.cuda.Event() for _ in range(2)]
+        mc.set_blocking(0)
+
+        def h2d(b):
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_d2h[b])          # the previous result of this buffer has left the device
+                dbuf[b][0].copy_(disk_in, non_blocking=True); dbuf[b][1].copy_(n_in, non_blocking=True)
+                ev_h2d[b].record(s_in)
+
+        def run_steps(k, sweep0):
+            for b in range(2):
+                ev_d2h[b].record(main_s)
+            h2d(0)
+            for i in range(k):
+                b = i & 1
+                if i + 1 < k:
+                    h2d(b ^ 1)
+                main_s.wait_event(ev_h2d[b])
+                mc.sweep(dbuf[b][0], dbuf[b][1], sweep0, S)
+                ev_swept[b].record(main_s)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_swept[b])
+                    hout[b][0].copy_(dbuf[b][0], non_blocking=True); hout[b][1].copy_(dbuf[b][1], non_blocking=True)
+                    ev_d2h[b].record(s_out)
+            main_s.wait_stream(s_out)
+
+        run_steps(2, sweep)
         torch.cuda.synchronize()
         mc.reset_counters()
         dist.barrier()
@@ -400,26 +452,32 @@ def main():
         t0 = time.perf_counter()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(args.steps):
-            disk.copy_(disk_host, non_blocking=True); n.copy_(n_host, non_blocking=True)
-            mc.sweep(disk, n, sweep, S)
-            disk_host.copy_(disk, non_blocking=True); n_host.copy_(n, non_blocking=True)
-            sweep += S
+        run_steps(args.steps, sweep)
         f1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         dist.barrier()
         ce = mc.counters()
+        # every step ran the same job: its result must be the same bits (and the serial, unpipelined answer)
+        same = bool(torch.equal(hout[0][0], hout[1][0]) and torch.equal(hout[0][1], hout[1][1])) if args.steps > 1 else True
+        disk.copy_(disk_in); n.copy_(n_in)
+        mc.set_blocking(1)
+        mc.sweep(disk, n, sweep, S)
+        same = same and bool(torch.equal(disk.cpu(), hout[(args.steps - 1) & 1][0]))
         et = torch.tensor([max(f0.elapsed_time(f1), wall * 1e3)], dtype=torch.float64, device="cuda")
-        etr = torch.tensor([ce["trials"]], dtype=torch.float64, device="cuda")
+        etr = torch.tensor([ce["trials"], 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
         dist.all_reduce(etr, op=dist.ReduceOp.SUM)
         e2e_ms = float(et.item())
-        nbytes = int(disk_host.numel() * 4 + n_host.numel() * 2) * n_ranks
-        e2e = {"value": float(etr.item()) / (e2e_ms * 1e-3), "unit": UNIT,
+        nbytes = int(disk_in.numel() * 4 + n_in.numel() * 2) * n_ranks
+        e2e = {"value": float(etr[0].item()) / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "ms_per_step": e2e_ms / args.steps,
-               "what": "per rank: H2D(slab disk, n) + pmc_sweep (NCCL ghost rows) + D2H(slab disk, n), pinned host buffers; max over ranks"}
+               "results_identical_to_serial_run": bool(etr[1].item() == 0.0),
+               "host_numa_binding": numa,
+               "what": "a stream of independent jobs; per step and rank: H2D(slab disk, n) + pmc_sweep (NCCL ghost rows) + "
+                       "D2H(slab disk, n), pinned host buffers, two device copies of the slab so that the copies of "
+                       "neighbouring steps overlap the sweeps; max over ranks"}
 
     cpu = None
     if rank == 0 and n_ranks == 1 and not args.no_cpu_baseline:
@@ -429,6 +487,7 @@ def main():
                "sample": f"{sample_wl}: {args.cpu_sweeps} sweeps from the lattice start in {dt:.1f} s; "
                          "oracle/pmc_oracle.c (the reference has no CPU path), OpenMP over same-colour cells"}
 
+    failed = False
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_ranks, "steps": args.steps,
@@ -451,9 +510,19 @@ def main():
             "gpu_launches": int(gpu_launches),
         }
         emit(line)
+        # a run that dropped a disk, produced an overlap or lost a particle is not a measurement
+        bad = [k for k, v in (("status", int(status)), ("lost", tot_lost), ("out_of_cell", chk_t[1].item()),
+                              ("overlaps_below_sigma", chk_t[2].item()), ("particles_missing", total_particles - N)) if v]
+        if e2e and e2e.get("results_identical_to_serial_run") is False:
+            bad.append("pipelined e2e result differs from the serial run")
+        if bad:
+            print("bench.py: invariant violated: " + ", ".join(bad), file=sys.stderr)
+            failed = True
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":
