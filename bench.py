@@ -8,7 +8,9 @@
 A "step" is one pass of the hot path over one batch: `sweeps_per_step` full MC sweeps
 (each = 4 checkerboard sub-sweeps + grid shift, start.cu:237-260) of the resident system.
 value  = trial moves actually executed (device-counted) / device time, inputs resident in HBM.
-e2e    = the same through pmc_run_host with HOST buffers: H2D(r) + assign + sweeps + D2H(disk, n).
+e2e    = the same through pmc_run_host with HOST buffers: H2D(r) + assign + sweeps + D2H(disk, n) per step,
+         steps being independent jobs alternated between two handles / two slab copies so that the copies of one
+         job overlap the sweeps of the other.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -377,32 +379,57 @@ def main():
     # end to end through the C-ABI with host buffers (single GPU only: slabs keep state on device)
     e2e = None
     if not args.no_e2e and n_ranks == 1:
+        # a stream of independent jobs through pmc_run_host (HOST buffers in, HOST buffers out), alternating between
+        # two handles on two streams, so that one job's H2D / D2H overlap the other job's sweeps
         del disk, n
         torch.cuda.empty_cache()
         r_host = mc.init_r().cpu().pin_memory()
-        disk_host = torch.empty((g.local_cells, 2, NMAX), dtype=torch.float32).pin_memory()
-        n_host = torch.empty((g.local_cells,), dtype=torch.int16).pin_memory()
-        mc.set_blocking(1)
-        for _ in range(2):
-            mc.run_host(r_host, 0, S, disk_host, n_host)
-        mc.reset_counters()
+        outs = [(torch.empty((g.local_cells, 2, NMAX), dtype=torch.float32).pin_memory(),
+                 torch.empty((g.local_cells,), dtype=torch.int16).pin_memory()) for _ in range(2)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        with torch.cuda.stream(streams[0]):
+            mc.use_torch_stream()
+        with torch.cuda.stream(streams[1]):
+            mc_b = pmc_b200.ParallelMC(N, phi=phi, sigma_d=SIGMA, cell_w=CELL_W, nmax=NMAX, n_M=N_M,
+                                       move_delta=delta, seed=SEED, cps_multiple=mult, device=local_rank)
+        hs = [mc, mc_b]
+        for m in hs:
+            m.set_blocking(0)
+
+        def run_jobs(k):
+            for i in range(k):
+                hs[i & 1].run_host(r_host, 0, S, *outs[i & 1])
+            for m in hs:
+                m.synchronize()
+
+        run_jobs(2)
+        for m in hs:
+            m.reset_counters()
         torch.cuda.synchronize()
+        f0 = torch.cuda.Event(enable_timing=True)
+        f1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         t0 = time.perf_counter()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            mc.run_host(r_host, 0, S, disk_host, n_host)
-        f1.record()
+        f0.record(streams[0])
+        streams[1].wait_event(f0)
+        run_jobs(args.steps)
+        for b in range(2):
+            f1[b].record(streams[b])
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        ce = mc.counters()
-        e2e_ms = max(f0.elapsed_time(f1), wall * 1e3)
-        e2e = {"value": ce["trials"] / (e2e_ms * 1e-3), "unit": UNIT,
+        e2e_trials = sum(m.counters()["trials"] for m in hs)
+        e2e_status = sum(m.counters()["status"] for m in hs)
+        e2e_ms = max(f0.elapsed_time(f1[0]), f0.elapsed_time(f1[1]), wall * 1e3)
+        same = bool(torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])) if args.steps > 1 else True
+        last = outs[(args.steps - 1) & 1]
+        e2e = {"value": e2e_trials / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(r_host.numel() * 4),
-               "d2h_bytes_per_step": int(disk_host.numel() * 4 + n_host.numel() * 2),
+               "d2h_bytes_per_step": int(last[0].numel() * 4 + last[1].numel() * 2),
                "ms_per_step": e2e_ms / args.steps,
-               "what": "pmc_run_host: H2D(r) + assign + sweeps + D2H(disk, n), pinned host buffers",
-               "n_sum_check": int(n_host.to(torch.int64).sum().item())}
+               "what": "a stream of independent jobs; per step pmc_run_host: H2D(r) + assign + sweeps + D2H(disk, n), pinned "
+                       "host buffers; jobs alternate between two handles on two streams (non-blocking pmc_run_host), so "
+                       "the copies of one job overlap the sweeps of the other",
+               "both_handles_same_result": same, "status": int(e2e_status),
+               "n_sum_check": int(last[1].to(torch.int64).sum().item())}
     elif not args.no_e2e:
         # slab runs: a stream of independent jobs, like the single-GPU leg (every step starts from the same host
         # input).  Per step and rank: H2D(slab disk, n) from pinned memory + pmc_sweep (S sweeps, NCCL ghost rows)
@@ -515,6 +542,8 @@ def main():
                               ("overlaps_below_sigma", chk_t[2].item()), ("particles_missing", total_particles - N)) if v]
         if e2e and e2e.get("results_identical_to_serial_run") is False:
             bad.append("pipelined e2e result differs from the serial run")
+        if e2e and (e2e.get("both_handles_same_result") is False or e2e.get("status") or e2e.get("n_sum_check", N) != N):
+            bad.append("e2e jobs disagree / lost particles")
         if bad:
             print("bench.py: invariant violated: " + ", ".join(bad), file=sys.stderr)
             failed = True

@@ -198,7 +198,11 @@ int  pmc_save_checkpoint(pmc_handle *h, const float *d_disk, const int16_t *d_n,
 int  pmc_load_checkpoint(pmc_handle *h, const char *path, float *d_disk, int16_t *d_n, uint64_t *sweep);
 
 /* ---- end-to-end with HOST buffers: H2D(r) -> assign -> n_sweeps sweeps -> D2H(disk, n).
- * This is what a start.cu-equivalent driver does around its loop (start.cu:227-262). */
+ * This is what a start.cu-equivalent driver does around its loop (start.cu:227-262).
+ * Blocking handles return when the results are in disk_host / n_host.  After pmc_set_blocking(h, 0) the call
+ * returns with the copies and the sweeps queued on the handle's stream: r_host, disk_host and n_host (pinned)
+ * belong to the library until pmc_synchronize(h); two handles on two streams then overlap the copies of one
+ * job with the sweeps of the other. */
 int  pmc_run_host(pmc_handle *h, const float *r_host, uint64_t sweep0, int n_sweeps,
                   float *disk_host, int16_t *n_host);
 

@@ -1021,10 +1021,10 @@ int pmc_run_host(pmc_handle *h, const float *r_host, uint64_t sweep0, int n_swee
     if (rc) return rc;
     CK(cudaMemcpyAsync(disk_host, h->run_disk, pmc_disk_bytes(h), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(n_host, h->run_n, pmc_n_bytes(h), cudaMemcpyDeviceToHost, h->stream));
-    h->blocking = 1;
-    rc = finish(h);                                 // synchronises; overflow / lost particles become the return code
-    h->blocking = was_blocking;
-    return rc;
+    // blocking handle (the default): synchronises; overflow / lost particles become the return code.
+    // pmc_set_blocking(h, 0): returns with everything queued on the handle's stream - the host buffers are the
+    // caller's until pmc_synchronize (two handles on two streams overlap one job's copies with the other's sweeps)
+    return finish(h);
 }
 
 // ------------------------------------------------------------------ initial configurations / trajectory / checkpoint

@@ -278,6 +278,37 @@ def test_run_host_round_trip():
     assert k == ko == 2 ** 14 and np.array_equal(bits(rg), bits(ro))
 
 
+def test_run_host_non_blocking_on_two_handles_matches_the_oracle():
+    """pmc_run_host after pmc_set_blocking(h, 0) queues H2D + assign + sweeps + D2H and returns; two handles on two
+    streams (bench.py's end-to-end leg) each deliver the oracle's bits after pmc_synchronize."""
+    import torch
+    import pmc_b200
+    from oracle import oracle as O
+    kw = dict(KW, seed=77)
+    N = 2 ** 16
+    o = O.Oracle(N, **kw)
+    r = o.init_r()
+    odisk, on = o.assign(r)
+    o.sweep(odisk, on, 0, 6)
+    rh = torch.from_numpy(r).pin_memory()
+    hs, outs = [], []
+    for _ in range(2):
+        with torch.cuda.stream(torch.cuda.Stream()):
+            mc = pmc_b200.ParallelMC(N, **kw)
+        mc.set_blocking(0)
+        g = mc.geom
+        hs.append(mc)
+        outs.append((torch.empty((g.local_cells, 2, 8), dtype=torch.float32).pin_memory(),
+                     torch.empty((g.local_cells,), dtype=torch.int16).pin_memory()))
+    for i in range(4):                                  # two jobs per handle, back to back
+        hs[i & 1].run_host(rh, 0, 6, *outs[i & 1])
+    for mc in hs:
+        mc.synchronize()
+    for (dh, nh), mc in zip(outs, hs):
+        assert np.array_equal(nh.numpy(), on) and np.array_equal(bits(dh.numpy()), bits(odisk))
+        assert mc.counters()["status"] == 0 and mc.counters()["trials"] == 2 * o.trials.value
+
+
 def test_disk_to_r_on_the_device_matches_the_oracle_and_the_host_variant():
     """pmc_disk_to_r (device scan + scatter) == oracle_disk_to_r (kernel.cu:497-507 order) == pmc_disk_to_r_host."""
     mc, o = pair(2 ** 16)
