@@ -36,7 +36,7 @@
  *     later shift, and "no pair with d2 < sigma_d^2" is an EXACT invariant of a trajectory
  *     (pmc_check: overlaps == 0, min_d2 >= sigma_d^2, bit for bit).  pmc_assign snaps the
  *     incoming coordinates to the grid (<= q/2 = 2.4e-7), pmc_schedule draws d on the grid,
- *     pmc_shift_cells rounds a caller-chosen d to it, move_delta is rounded down to it.
+ *     pmc_shift_cells rounds a caller-chosen d to it, trial displacements are multiples of it (below).
  *   - compile-time #defines (start.cu:14-24) become the runtime pmc_params.
  *   - cuRAND XORWOW seeded identically on every launch (subsweep.h:259) becomes a
  *     counter-based Philox4x32-10 stream keyed on (seed, sweep, cell, trial).
@@ -82,8 +82,11 @@ typedef struct pmc_params {
 } pmc_params;
 
 /* Trial displacement (make_move subsweep.h:60-71; reference: x + curand_normal * sigma per axis):
- *   PMC_PROPOSAL_UNIFORM   uniform in the square [-move_delta, move_delta]^2 on the coordinate grid: integer
- *                          arithmetic only, CPU oracle and GPU agree BIT FOR BIT, served by the fast kernel;
+ *   PMC_PROPOSAL_UNIFORM   uniform in the square on the coordinate grid: 4096 equally spaced levels per axis,
+ *                          (2k - 4095) * A * q with k a 12-bit field of the trial's Philox word and
+ *                          A = floor(move_delta / (4095 q)), i.e. half-width 4095 A q, at most 4095 q (0.002 at
+ *                          w = 2) below move_delta (pmc_geometry.move_delta reports it; move_delta >= 4095 q is
+ *                          required).  Exact arithmetic only: CPU oracle and GPU agree BIT FOR BIT; fast kernel;
  *   PMC_PROPOSAL_GAUSSIAN  the reference's N(0, move_delta^2) per axis (Box-Muller on the Philox words, rounded
  *                          to the grid, signs from separate bits: exactly symmetric).  Uses logf / sincospif, so
  *                          a CPU and the GPU agree statistically only (tests: acceptance and contact value within

@@ -20,7 +20,7 @@ class Geom(C.Structure):
         ("nmax", C.c_int), ("n_M", C.c_int), ("w", C.c_float), ("L", C.c_float),
         ("half_L", C.c_float), ("sigma", C.c_float), ("sigma2", C.c_float),
         ("delta", C.c_float), ("dscale", C.c_float), ("L_box", C.c_double),
-        ("seed", C.c_uint64), ("K", C.c_int), ("M", C.c_int), ("proposal", C.c_int),
+        ("seed", C.c_uint64), ("K", C.c_int), ("M", C.c_int), ("proposal", C.c_int), ("A", C.c_int),
     ]
 
 

@@ -52,7 +52,9 @@ int oracle_make_geom(int64_t n_particles, float phi, float sigma_d, float cell_w
     double q = ldexp(1.0, ex - 24);
     double K = nearbyint(w_d / q);               /* cell width in grid units, < 2^23 */
     double M = floor((double)move_delta / q);    /* proposal half-width in grid units */
-    if (M < 1.0 || M >= 4194304.0 || (double)move_delta > w_d) return 1;
+    /* the uniform proposal has 4096 levels (2k - 4095) * A * q per axis, A = floor(M / 4095) >= 1 */
+    if (M < 4095.0 || M >= 4194304.0 || (double)move_delta > w_d) return 1;
+    if (2.0 * floor(M / 4095.0) * q * ldexp(1.0, 137) >= ldexp(1.0, 127)) return 1;   /* the CUDA path's scale factor must be a finite float */
     memset(g, 0, sizeof(*g));
     g->n_particles = n_particles;
     g->cps = (int)cps;
@@ -62,6 +64,7 @@ int oracle_make_geom(int64_t n_particles, float phi, float sigma_d, float cell_w
     g->w = (float)(K * q);
     g->K = (int)K;
     g->M = (int)M;
+    g->A = (int)floor(M / 4095.0);
     g->L_box = (double)cps * (double)g->w;
     g->L = (float)g->L_box;
     g->half_L = g->L / 2.0f;
@@ -271,7 +274,7 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
     if (cnt == 0) return;                                 /* subsweep.h:252-254 */
     float *X = disk + cell * 2 * nm, *Y = X + nm;         /* cpy_to_Dsh subsweep.h:18-27 */
     /* all random words of this cell's sub-sweep.  Uniform proposal: ONE 32-bit word per trial
-     * (dx: bits 20-31, dy: bits 8-19, shuffle: bits 0-7), one Philox call feeds four trials.
+     * (shuffle: bits 24-31, dx: bits 12-23, dy: bits 0-11), one Philox call feeds four trials.
      * Gaussian proposal: two words per trial (23 + 1 bits per axis), one call feeds two trials. */
     uint32_t words[2 * 64 + 4];
     const int per_call = g->proposal == 1 ? 2 : 4;
@@ -281,7 +284,7 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
      * cell's slots, written back with the cell like the reference's D_sh.  Only the first
      * min(n_M, cnt) positions are ever visited by the trial loop, so the shuffle stops there
      * (partial Fisher-Yates: positions 0..k-1 hold an ordered sample without replacement).  Step s
-     * takes its random bits from the low byte(s) of trial s's word(s): 8 bits (uniform proposal: the
+     * takes its random bits from trial s's word(s): the top byte (uniform proposal: 8 bits, the
      * choice among m <= 8 remaining slots is uniform to 1 part in 256 / m) or 16 bits (Gaussian).
      * Which disk a trial moves never depends on the positions, so detailed balance is not affected. */
     int steps = g->n_M < cnt ? g->n_M : cnt;
@@ -292,23 +295,24 @@ static void subsweep_cell(const oracle_geom *g, float *disk, const int16_t *n,
             uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
             j = s + (int)((b16 * (uint32_t)(cnt - s)) >> 16);
         } else {
-            j = s + (int)(((words[s] & 0xFFu) * (uint32_t)(cnt - s)) >> 8);
+            j = s + (int)(((words[s] >> 24) * (uint32_t)(cnt - s)) >> 8);
         }
         float t;
         t = X[s]; X[s] = X[j]; X[j] = t;
         t = Y[s]; Y[s] = Y[j]; Y[j] = t;
     }
-    const uint32_t nM2 = 2u * (uint32_t)g->M + 1u;
     for (int s = 0; s < g->n_M; s++) {                    /* subsweep.h:279 */
         uint32_t ra = g->proposal == 1 ? words[2 * s] : words[s], rb = g->proposal == 1 ? words[2 * s + 1] : 0u;
         int slot = s % cnt;                               /* i = (i+1) mod atom_counts, subsweep.h:291-296 */
-        /* make_move subsweep.h:60-71; proposal = uniform in the square on
-         * the coordinate grid: m * q per axis with m = floor((2 r12 + 1) * (2M+1) / 2^13) - M from
-         * a 12-bit field r12 of the word.  P(m) == P(-m) exactly: r12 -> 2^12 - 1 - r12 maps the
-         * odd number 2 r12 + 1 to 2^13 - (2 r12 + 1), and odd * odd / 2^13 is never an integer, so
-         * the floor maps m to -m.  A symmetric proposal is all detailed balance needs.  x + m*q is exact. */
-        int mx = (int)((((uint64_t)(ra >> 20) * 2u + 1u) * nM2) >> 13) - g->M;
-        int my = (int)((((uint64_t)((ra >> 8) & 0xFFFu) * 2u + 1u) * nM2) >> 13) - g->M;
+        /* make_move subsweep.h:60-71; proposal = uniform in the square on the
+         * coordinate grid: 4096 equally spaced levels m * q per axis, m = (2k - 4095) * A with k a 12-bit
+         * field of the word (x: bits 12-23, y: bits 0-11; the shuffle took bits 24-31) and A = floor(M / 4095):
+         * half-width 4095 A q, at most 4095 q below move_delta.  P(m) == P(-m) exactly (k -> 4095 - k); a
+         * symmetric proposal is all detailed balance needs.  x + m*q is exact.  (The GPU reads the field in
+         * place as the denormal float k * 2^-137 and evaluates fmaf(k 2^-137, 2 A q 2^137, x - 4095 A q):
+         * the same number, every step exact.) */
+        int mx = (2 * (int)((ra >> 12) & 0xFFFu) - 4095) * g->A;
+        int my = (2 * (int)(ra & 0xFFFu) - 4095) * g->A;
         if (g->proposal == 1) {
             /* the reference's proposal, make_move subsweep.h:60-71: x + curand_normal * sigma per axis.
              * Box-Muller on bits 8..30 of the two words (radius from ra, angle in the first quadrant from

@@ -60,11 +60,12 @@ typedef struct {
     double  L_box;      /* cps * (double)w */
     uint64_t seed;
     int     K;          /* w / q: cell width in grid units (< 2^23) */
-    int     M;          /* delta / q: proposals are m * q, m uniform-symmetric in [-M, M] */
+    int     M;          /* delta / q (>= 4095): the Gaussian proposal's sigma in grid units */
     int     proposal;   /* 0: uniform in the square [-delta, delta]^2 (default, bit-exact on CPU and GPU);
                          * 1: the reference's Gaussian, N(0, delta^2) per axis (make_move subsweep.h:64
                          *    curand_normal * sigma), rounded to the grid; libm transcendentals, so CPU and
                          *    GPU agree statistically, not bit for bit */
+    int     A;          /* uniform proposal: m = (2k - 4095) * A, k a 12-bit field; A = M / 4095, half-width 4095 A q */
 } oracle_geom;
 
 /* a1: #define block start.cu:14-27 -> runtime geometry.  cps_multiple: 2 normally. */

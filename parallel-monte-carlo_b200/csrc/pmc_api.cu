@@ -173,12 +173,15 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     (void)frexp(2.0 * w_d, &ex);
     const double q = ldexp(1.0, ex - 24);
     const double K = nearbyint(w_d / q), M = floor((double)p.move_delta / q);
-    if (M < 1.0 || M >= 4194304.0 || (double)p.move_delta > w_d) return PMC_E_INVALID;
+    // the uniform proposal has 4096 levels (2k - 4095) * A * q per axis, A = floor(M / 4095) >= 1
+    if (M < 4095.0 || M >= 4194304.0 || (double)p.move_delta > w_d) return PMC_E_INVALID;
+    const double A = floor(M / 4095.0);
+    if (2.0 * A * q * ldexp(1.0, 137) >= ldexp(1.0, 127)) return PMC_E_INVALID;     // dstep must be a finite float (w >= 4 with delta ~ w/2)
     DevGeom g;
     memset(&g, 0, sizeof(g));
     g.cps = (int)cps;
     g.w = (float)(K * q);
-    g.K = (int)K; g.M = (int)M; g.nM2 = 2u * (unsigned)M + 1u; g.mofs = (float)(8388608.0 + M);
+    g.K = (int)K; g.M = (int)M; g.A = (int)A; g.dstep = (float)(2.0 * A * q * ldexp(1.0, 137)); g.doff = (float)(4095.0 * A * q);
     g.L_box = (double)cps * (double)g.w;
     g.L = (float)g.L_box;
     g.half_L = g.L / 2.0f;
@@ -205,7 +208,7 @@ static int derive_geometry(const pmc_params &p_in, pmc_params *p_out, DevGeom *g
     pmc_geometry pg;
     memset(&pg, 0, sizeof(pg));
     pg.n_particles = p.n_particles; pg.cps = g.cps; pg.n_cells = cps * cps; pg.nmax = PMC_NMAX;
-    pg.n_M = p.n_M; pg.w = g.w; pg.L = g.L; pg.sigma_d = p.sigma_d; pg.move_delta = (float)(M * q); pg.grid_q = (float)q;
+    pg.n_M = p.n_M; pg.w = g.w; pg.L = g.L; pg.sigma_d = p.sigma_d; pg.move_delta = (float)((p.proposal == PMC_PROPOSAL_GAUSSIAN ? M : 4095.0 * A) * q); pg.grid_q = (float)q;
     pg.row0 = g.row0; pg.rows = g.rows; pg.ghost_rows = g.ghost;
     pg.local_cells = (long long)g.local_rows * g.cps;
     if (p_out) *p_out = p;
@@ -257,7 +260,7 @@ int pmc_create(const pmc_params *pp, pmc_handle **out)
         Geom4 &q = h->g4;
         q.cps = g.cps; q.row0 = g.row0; q.rows = g.rows; q.wrap_y = g.wrap_y;
         pmc4_alloc_shape(g.cps, g.rows, &q.CH, &q.ROWS, &q.FW, &q.FH);
-        q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale; q.nM2 = g.nM2; q.mofs = g.mofs;
+        q.w = g.w; q.hw = 0.5f * g.w; q.sigma2 = g.sigma2; q.dscale = g.dscale; q.dstep = g.dstep; q.doff = g.doff;
         q.seed_lo = g.seed_lo; q.seed_hi = g.seed_hi;
         q.try_ns4 = (double)p.n_particles / ((double)g.cps * (double)g.cps) < 2.5;   // a performance hint only
         for (int r = 0; r < 10; r++) { q.pk0[r] = g.seed_lo + (unsigned)r * 0x9E3779B9u; q.pk1[r] = g.seed_hi + (unsigned)r * 0xBB67AE85u; }

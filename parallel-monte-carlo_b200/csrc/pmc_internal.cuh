@@ -24,8 +24,8 @@ struct DevGeom {
     float dscale;           // q: the coordinate grid quantum (a power of two; pmc.h "coordinate grid")
     int K;                  // w / q: cell width in grid units (< 2^23)
     int M;                  // move_delta / q: trial displacements are m * q, m in [-M, M]
-    unsigned nM2;           // 2M + 1
-    float mofs;             // 2^23 + M (exact): turns the biased mantissa trick into m
+    int A;                  // uniform proposal: displacements are (2k - 4095) * A * q, k a 12-bit field; A = M / 4095
+    float dstep, doff;      // 2 A q * 2^137 and 4095 A q: p = fmaf(grid_disp, dstep, x - doff) (grid_disp_x / _y below)
     int proposal;           // PMC_PROPOSAL_UNIFORM / PMC_PROPOSAL_GAUSSIAN
     float L;
     float half_L;
@@ -111,8 +111,7 @@ struct Geom4 {
     int ROWS;                   // allocated rows
     int FW, FH;                 // crowded-cell flag grid: words per row, rows
     float w, hw, sigma2, dscale;    // dscale = q, the coordinate grid quantum
-    unsigned nM2;                   // 2M + 1 trial displacements per axis (DevGeom)
-    float mofs;                     // 2^23 + M
+    float dstep, doff;              // trial proposal p = fmaf(grid_disp, dstep, x - doff) (DevGeom)
     unsigned seed_lo, seed_hi;
     int try_ns4;                // mean occupancy is low: worth scanning for tiles whose cells all hold <= 4 disks
     unsigned pk0[10], pk1[10];  // Philox round keys seed + r * (0x9E3779B9, 0xBB67AE85): constant-bank operands
@@ -168,22 +167,17 @@ __device__ __forceinline__ void philox4x32_10_keys(uint32_t c0, uint32_t c1, uin
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-// Trial displacement in grid units (make_move subsweep.h:60-71, proposal uniform in the square on
-// the coordinate grid): m = floor((2 r12 + 1) * (2M+1) / 2^13) - M from a 12-bit field r12 of the trial's
-// random word (exactly symmetric, P(m) == P(-m)), as an exact float and without I2F: with the field
-// in the top 12 bits, (r & 0xFFF00000) | 0x80000 = 2^19 (2 r12 + 1), the high half of the product with
-// 2M+1 is floor(..), and OR-ed into the mantissa of 2^23 it is a float.  _hi: bits 20-31 (x), _lo: bits 8-19 (y).
-// Identical to oracle/pmc_oracle.c subsweep_cell.
-__device__ __forceinline__ float grid_disp_hi(uint32_t r, unsigned nM2, float mofs)
-{
-    // t <= 2M < 2^23 (pmc_create: M < 2^22): OR-ing it into the mantissa of 2^23 is the exact float 2^23 + t
-    const uint32_t t = __umulhi((r & 0xFFF00000u) | 0x80000u, nM2);
-    return __fadd_rn(__uint_as_float(t | 0x4B000000u), -mofs);
-}
-__device__ __forceinline__ float grid_disp_lo(uint32_t r, unsigned nM2, float mofs)
-{
-    return grid_disp_hi(r << 12, nM2, mofs);
-}
+// Trial displacement (make_move subsweep.h:60-71, proposal uniform in the square on the coordinate grid):
+// 4096 equally spaced levels m * q per axis, m = (2k - 4095) * A, k a 12-bit field of the trial's random word
+// (x: bits 12-23, y: bits 0-11, shuffle: bits 24-31), A = floor(M / 4095); k -> 4095 - k maps m -> -m, so the
+// proposal is exactly symmetric.  No integer -> float conversion: a 12-bit field sitting in bits 12-23 of a word
+// whose other bits are zero IS the float k * 2^-137 (bits 0-22 are a denormal's mantissa, bit 23 continues it
+// linearly), FMA units take denormals at full speed, and
+//     p = fmaf(k * 2^-137, dstep, x - doff),   dstep = 2 A q * 2^137,   doff = 4095 A q
+// is x + m q with every step exact (x - doff is on the grid and below 2^24 q; the product is exact inside the FMA).
+// x: one LOP3; y: one shift + one LOP3.  Identical to oracle/pmc_oracle.c subsweep_cell.
+__device__ __forceinline__ float grid_disp_x(uint32_t r) { return __uint_as_float(r & 0x00FFF000u); }
+__device__ __forceinline__ float grid_disp_y(uint32_t r) { return __uint_as_float((r << 12) & 0x00FFF000u); }
 
 // The reference's Gaussian proposal (make_move subsweep.h:60-71: x + curand_normal * sigma per axis) in grid
 // units: Box-Muller on bits 8..30 of the two words, signs from bit 31 (oracle subsweep_cell, proposal == 1).

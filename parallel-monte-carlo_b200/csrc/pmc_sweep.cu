@@ -347,7 +347,10 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
 
     // ------------------------------------------------------------ the sub-sweeps
     unsigned my_trials = 0, my_acc = 0;
-    const float sigma = g.sigma, sigma2 = g.sigma2, dscale = g.dscale;
+    const float sigma = g.sigma, sigma2 = g.sigma2;
+    // Gaussian: m * q + x (m from gauss_disp, in grid units); uniform: fmaf(grid_disp, dstep, x - doff)
+    const bool gauss_p = g.proposal == PMC_PROPOSAL_GAUSSIAN;
+    const float dscale = gauss_p ? g.dscale : g.dstep, doff = gauss_p ? 0.0f : g.doff;
     const int bq = tid / NAX, aq = tid - bq * NAX;  // fixed thread -> (column, row) of the active lattice
 
 #pragma unroll 1
@@ -427,7 +430,7 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     const uint32_t b16 = ((rw[2 * s] & 0xFFu) << 8) | (rw[2 * s + 1] & 0xFFu);
                     const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
                     const int jj = s + (gauss ? (int)((b16 * (uint32_t)mrem) >> 16)
-                                              : (int)(((rw[s] & 0xFFu) * (uint32_t)mrem) >> 8));
+                                              : (int)(((rw[s] >> 24) * (uint32_t)mrem) >> 8));
                     const float tx = ox[s], ty = oy[s];
                     float nx = tx, ny = ty;
 #pragma unroll
@@ -446,10 +449,10 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
                     const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
                     const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-                    float mx = grid_disp_hi(rw[s], g.nM2, g.mofs), my = grid_disp_lo(rw[s], g.nM2, g.mofs);
+                    float mx = grid_disp_x(rw[s]), my = grid_disp_y(rw[s]);
                     if (gauss) gauss_disp(rw[2 * s], rw[2 * s + 1], g.M, mx, my);
-                    const float px = __fmaf_rn(mx, dscale, x);     // make_move subsweep.h:60-71
-                    const float py = __fmaf_rn(my, dscale, y);
+                    const float px = __fmaf_rn(mx, dscale, __fadd_rn(x, -doff));     // make_move subsweep.h:60-71
+                    const float py = __fmaf_rn(my, dscale, __fadd_rn(y, -doff));
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot
@@ -500,7 +503,7 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                         const uint32_t rb = h ? r[3] : r[1];
                         const uint32_t b16 = ((ra & 0xFFu) << 8) | (rb & 0xFFu);
                         const int jj = s + (gauss ? (int)((b16 * (uint32_t)(cnt - s)) >> 16)
-                                                  : (int)(((ra & 0xFFu) * (uint32_t)(cnt - s)) >> 8));
+                                                  : (int)(((ra >> 24) * (uint32_t)(cnt - s)) >> 8));
                         float *ps = slot_ptr(s), *pj = slot_ptr(jj);
                         const float xs = ps[0], ys = ps[2 * PL * 4], xj = pj[0], yj = pj[2 * PL * 4];
                         ps[0] = xj; ps[2 * PL * 4] = yj; pj[0] = xs; pj[2 * PL * 4] = ys;
@@ -517,10 +520,10 @@ sweep_tile_kernel(const float4 *din, const int16_t *nin, float4 *dout, int16_t *
                     float *fx = slot_ptr(it), *fy = fx + 2 * PL * 4;
                     it = (it + 1 >= cnt) ? 0 : it + 1;
                     const float x = *fx, y = *fy;
-                    float mx = grid_disp_hi(ra, g.nM2, g.mofs), my = grid_disp_lo(ra, g.nM2, g.mofs);
+                    float mx = grid_disp_x(ra), my = grid_disp_y(ra);
                     if (gauss) gauss_disp(ra, rb, g.M, mx, my);
-                    const float px = __fmaf_rn(mx, dscale, x);
-                    const float py = __fmaf_rn(my, dscale, y);
+                    const float px = __fmaf_rn(mx, dscale, __fadd_rn(x, -doff));
+                    const float py = __fmaf_rn(my, dscale, __fadd_rn(y, -doff));
                     my_trials += owned ? 1u : 0u;
                     float m = neighbours_min_d2(px, py);
                     if (m >= 0.0f) {

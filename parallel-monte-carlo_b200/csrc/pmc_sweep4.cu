@@ -287,7 +287,7 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
 {
     constexpr int PITCH = TL::PITCH, PLC = TL::PLC;
     const int cps = g.cps;
-    const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dscale = g.dscale;
+    const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dstep = g.dstep, doff = g.doff;
     // which cells this colour works on (SweepArgs::colour_word, planned on the host: tile-independent).
     // Cells closer than lo to the region edge are stale or irrelevant; (i0, j0) = first active cell.
     const unsigned cw = a.colour_word[k];
@@ -330,14 +330,14 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
 
     float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
     float oy[8] = { p1.x, p1.y, p1.z, fabsf(p1.w), p2.z, p2.w, p3.z, p3.w };     // y3 carries the "5 or more" flag in its sign
-    // ONE Philox call per cell and sub-sweep: word s feeds trial s (dx: bits 20-31, dy: bits 8-19, shuffle: bits 0-7)
+    // ONE Philox call per cell and sub-sweep: word s feeds trial s (shuffle: bits 24-31, dx: bits 12-23, dy: bits 0-11)
     uint32_t rw[4];
     philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.pk0, g.pk1, rw[0], rw[1], rw[2], rw[3]);
     // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
-        const int jj = s + (int)(((rw[s] & 0xFFu) * (uint32_t)mrem) >> 8);
+        const int jj = s + (int)(((rw[s] >> 24) * (uint32_t)mrem) >> 8);
         const float tx = ox[s], ty = oy[s];
         float nx = tx, ny = ty;
 #pragma unroll
@@ -356,8 +356,8 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const bool cB = (s == 3) && (cnt == 2);             // slot == 1 (only s = 3, cnt = 2)
         const float x = cA ? ox[s] : (cB ? ox[1] : ox[0]);
         const float y = cA ? oy[s] : (cB ? oy[1] : oy[0]);
-        const float px = __fmaf_rn(grid_disp_hi(rw[s], g.nM2, g.mofs), dscale, x);      // make_move subsweep.h:60-71
-        const float py = __fmaf_rn(grid_disp_lo(rw[s], g.nM2, g.mofs), dscale, y);
+        const float px = __fmaf_rn(grid_disp_x(rw[s]), dstep, __fadd_rn(x, -doff));      // make_move subsweep.h:60-71
+        const float py = __fmaf_rn(grid_disp_y(rw[s]), dstep, __fadd_rn(y, -doff));
         bool inb;
         float m = neighbours_min_d2(px, py, inb);
         // own cell (calculate_energy_in_cell subsweep.h:105-117), j != slot

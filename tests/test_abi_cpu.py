@@ -118,7 +118,7 @@ def test_c_driver_command_line_replaces_the_define_block(built, tmp_path):
     import re
     import subprocess
     exe = _build_start_driver()
-    common = ["--N", "4096", "--phi", "0.6", "--w", "2.2", "--n-M", "4", "--delta", "0.15", "--seed", "77", "--sigma-d", "1.0", "--nmax", "8"]
+    common = ["--N", "4096", "--phi", "0.6", "--w", "2.0", "--n-M", "4", "--delta", "0.15", "--seed", "77", "--sigma-d", "1.0", "--nmax", "8"]
     ck, dump = str(tmp_path / "a.ckpt"), str(tmp_path / "traj.txt")
     a = subprocess.run([exe] + common + ["--passes", "6", "--trace", "2", "--checkpoint", ck, "--dump", dump, "--dump-every", "3", "--verify"],
                        capture_output=True, text=True, timeout=120)

@@ -249,13 +249,23 @@ def test_no_overlap_invariant_is_exact_and_pair_distances_survive_shifts(phi):
 
 
 def test_trial_displacements_are_symmetric_on_the_grid():
-    """m = floor((2 r24 + 1) * (2M+1) / 2^25) - M: P(m) == P(-m) exactly."""
-    for M in (1, 5, 209715, 838860):
-        nM2 = 2 * M + 1
-        r = np.arange(2 ** 24, dtype=np.uint64)
-        m = (((2 * r + 1) * nM2) >> 25).astype(np.int64) - M
-        cnt = np.bincount(m + M, minlength=nM2)
-        assert m.min() == -M and m.max() == M and np.array_equal(cnt, cnt[::-1])
+    """m = (2k - 4095) * A over the 12-bit field k: 4096 equally spaced levels, P(m) == P(-m) exactly, half-width
+    4095 A q within 4095 q of move_delta; the float construction of the CUDA path (the field read in place as
+    the denormal k * 2^-137, times 2 A q 2^137 inside one fmaf) gives the same numbers."""
+    k = np.arange(4096, dtype=np.int64)
+    for delta in (0.08, 0.1, 0.4, 0.7):
+        o = O.Oracle(4096, **dict(KW, move_delta=delta))
+        q, A, M = float(o.g.dscale), o.g.A, o.g.M
+        assert A == M // 4095 >= 1 and M - 4095 < 4095 * A <= M
+        m = (2 * k - 4095) * A
+        assert np.array_equal(np.sort(m), np.sort(-m)) and m.max() == 4095 * A and len(np.unique(m)) == 4096
+        f = (k << 12).astype(np.uint32).view(np.float32)                # bits 12-23 of an otherwise zero word
+        assert np.array_equal(f.astype(np.float64), k * 2.0 ** -137)
+        dstep = np.float32(2.0 * A * q * 2.0 ** 137)
+        assert np.isfinite(dstep) and float(dstep) == 2.0 * A * q * 2.0 ** 137
+        assert np.array_equal(f.astype(np.float64) * float(dstep) - 4095.0 * A * q, m * q)
+    with pytest.raises(ValueError):
+        O.Oracle(4096, **dict(KW, move_delta=0.001))        # fewer than 4095 grid steps: no room for 4096 levels
 
 
 # ---------------------------------------------------------------- full protocol invariants (config 1, shortened)
