@@ -64,11 +64,11 @@ struct SweepArgs {
     int tx, ty, hx, hy;
     unsigned lo_x, lo_y;
     int sh_nseg, sh_inv, sh_inv2;   // shift_store_pass: kNT / tx and the multiply-shift reciprocals of tx and of kNT / tx
-    // per colour, everything about "which cells are active" that does not depend on the tile (tiles start
-    // on even columns / rows): bits 0-3 i0, 4-7 j0 (first active column / row of the region), 8-11 / 12-15
-    // lo_x / lo_y, 16-23 / 24-31 chunk offset of the first active cell / of its left neighbour in the staged
-    // box (lane part excluded)
-    unsigned colour_word[4];
+    // per colour, everything about "which cells are active" that depends on the tile only through the parity of its
+    // first owned column / row (tile extents may be odd): bits 0-3 i0, 4-7 j0 (first active column / row of the
+    // region), 8-11 / 12-15 lo_x / lo_y, 16-23 / 24-31 chunk offset of the first active cell / of its left neighbour
+    // in the staged box (lane part excluded).  Index = (row0 & 1) * 8 + (col0 & 1) * 4 + k.
+    unsigned colour_word[16];
     // result-invariant path selection (pmc_set_tuning; tests use it to drive the rare paths): 8 treat every tile
     // as crowded, 16 never use the 4-slot instantiation, 64 full halo for every colour order.
     // Builds with -DPMC_DEBUG additionally honour the phase-isolation bits (env PMC_DBG_SKIP) that DO change

@@ -277,6 +277,7 @@ struct TileCtx {
     int X0, Y0;             // internal array coordinates of region (0, 0)
     int tx, ty;             // nominal owned extent of this tiling
     int wraps;              // the region reaches beyond the box: global cell coordinates need the periodic wrap
+    int cwsel;              // which set of SweepArgs::colour_word: (row0 & 1) * 8 + (col0 & 1) * 4
     int edge;               // owned cells of this tile have periodic images in the margins
 };
 
@@ -288,9 +289,9 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     constexpr int PITCH = TL::PITCH, PLC = TL::PLC;
     const int cps = g.cps;
     const float w = g.w, hw = g.hw, sigma2 = g.sigma2, dstep = g.dstep, doff = g.doff;
-    // which cells this colour works on (SweepArgs::colour_word, planned on the host: tile-independent).
+    // which cells this colour works on (SweepArgs::colour_word, planned on the host per parity of the tile origin).
     // Cells closer than lo to the region edge are stale or irrelevant; (i0, j0) = first active cell.
-    const unsigned cw = a.colour_word[k];
+    const unsigned cw = a.colour_word[t.cwsel + k];
     const int i0 = (int)(cw & 15u), j0 = (int)((cw >> 4) & 15u), lox = (int)((cw >> 8) & 15u), loy = (int)((cw >> 12) & 15u);
     const int i = i0 + 2 * aq, j = j0 + 2 * bq;
     if (!(i < t.RX - lox && j < t.RY - loy)) return;
@@ -617,6 +618,7 @@ __device__ __forceinline__ bool process_tile(const CUtensorMap *tmap_p, float4 *
     t.ry0 = row0 - HY - eyl;
     t.X0 = t.rx0 + kMX; t.Y0 = t.ry0 + kMY;         // region (0, 0) in internal array coordinates (>= 0)
     t.xs = t.X0 & 1;
+    t.cwsel = ((row0 & 1) << 3) | ((col0 & 1) << 2);
     t.ox0 = HX + exl; t.oy0 = HY + eyl;
     t.nox = min(tx, cps - col0); t.noy = min(ty, g.rows - row0);
     const int Xb0 = t.X0 - t.xs;                    // first column of the staged box
@@ -953,25 +955,30 @@ void pmc4_plan_sweep(SweepArgs &a, int full_halo)
         a.lo_y |= (unsigned)(1 + lasy[0] - lasy[k]) << (4 * k);
     }
     const int ex = (a.shift_on && a.shift_f == 0) ? 1 : 0, ey = (a.shift_on && a.shift_f == 1) ? 1 : 0;
-    {   // region (0, 0) sits at column col0 - hx - exl, row row0 - hy - eyl with col0, row0 (and the slab origin) even
+    {   // region (0, 0) sits at column col0 - hx - exl, row row0 - hy - eyl (the slab origin is even); tile extents
+        // may be odd, so the parities of col0 / row0 alternate from tile to tile: one set of words per parity pair
         const int sdir = (a.shift_d <= 0.0f) ? -1 : 1;
         const int exl = ex && sdir < 0, eyl = ey && sdir < 0;
-        const int xs = (a.hx + exl) & 1;                                    // parity of the region's first internal column (kMX even)
-        for (int k = 0; k < 4; k++) {
-            const int lox = (int)((a.lo_x >> (4 * k)) & 15u), loy = (int)((a.lo_y >> (4 * k)) & 15u);
-            const int pi = (a.offx[k] + a.hx + exl) & 1, pj = (a.offy[k] + a.hy + eyl) & 1;
-            const int i0 = lox + ((pi - lox) & 1), j0 = loy + ((pj - loy) & 1);
-            const int isu = i0 + xs, par = isu & 1;
-            const int off_own = j0 * BoxF::PITCH + par * BoxF::HB + (isu >> 1);
-            const int off_left = j0 * BoxF::PITCH + (1 - par) * BoxF::HB + ((isu - 1) >> 1);
-            a.colour_word[k] = (unsigned)i0 | ((unsigned)j0 << 4) | ((unsigned)lox << 8) | ((unsigned)loy << 12) |
-                               ((unsigned)off_own << 16) | ((unsigned)off_left << 24);
-        }
+        for (int py = 0; py < 2; py++)
+            for (int px = 0; px < 2; px++) {
+                const int xs = (a.hx + exl + px) & 1;                       // parity of the region's first internal column (kMX even)
+                for (int k = 0; k < 4; k++) {
+                    const int lox = (int)((a.lo_x >> (4 * k)) & 15u), loy = (int)((a.lo_y >> (4 * k)) & 15u);
+                    const int pi = (a.offx[k] + a.hx + exl + px) & 1, pj = (a.offy[k] + a.hy + eyl + py) & 1;
+                    const int i0 = lox + ((pi - lox) & 1), j0 = loy + ((pj - loy) & 1);
+                    const int isu = i0 + xs, par = isu & 1;
+                    const int off_own = j0 * BoxF::PITCH + par * BoxF::HB + (isu >> 1);
+                    const int off_left = j0 * BoxF::PITCH + (1 - par) * BoxF::HB + ((isu - 1) >> 1);
+                    a.colour_word[py * 8 + px * 4 + k] = (unsigned)i0 | ((unsigned)j0 << 4) | ((unsigned)lox << 8) | ((unsigned)loy << 12) |
+                                                         ((unsigned)off_own << 16) | ((unsigned)off_left << 24);
+                }
+            }
     }
     // columns: region tx + 2 hx + ex, of which all but the two edge columns can be active in colour 0: <= 32;
     // rows: region ty + 2 hy + ey <= kSYB
-    a.tx = (34 - 2 * a.hx - ex) & ~1;
-    a.ty = (kSYB - 2 * a.hy - ey) & ~1;
+    // (both extents are odd in sweeps that shift along x: 34 - 2 hx - 1 columns, 33 - 2 hy rows)
+    a.tx = 34 - 2 * a.hx - ex;
+    a.ty = kSYB - 2 * a.hy - ey;
     // shift_store_pass, shift along y: thread -> (segment, column) = (tid / tx, tid % tx) and rows per segment
     // = ceil(ty / nseg) by exact multiply-shifts (tid < 256, ty + nseg <= 64)
     a.sh_nseg = kNT / a.tx;
