@@ -337,13 +337,13 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-        const int mrem = cnt > s ? cnt - s : 1;             // s >= cnt: no-op (jj == s)
-        const int jj = s + (int)(((rw[s] >> 24) * (uint32_t)mrem) >> 8);
+        // jd = jj - s = ((r >> 24) * (cnt - s)) >> 8 as the high half of one product; s >= cnt: 0 remaining slots, jd = 0 (no-op)
+        const int jd = (int)__umulhi(rw[s] & 0xFF000000u, (uint32_t)max(cnt - s, 0));
         const float tx = ox[s], ty = oy[s];
         float nx = tx, ny = ty;
 #pragma unroll
         for (int q = s + 1; q < NS; q++) {
-            const bool p = (jj == q);
+            const bool p = (jd == q - s);
             nx = p ? ox[q] : nx; ny = p ? oy[q] : ny;
             ox[q] = p ? tx : ox[q]; oy[q] = p ? ty : oy[q];
         }
