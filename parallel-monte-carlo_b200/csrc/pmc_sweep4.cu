@@ -135,7 +135,7 @@ __device__ __forceinline__ float2 pair2(float qx0, float qx1, float qy0, float q
 // smallest squared distance between the trial point (negated, in this cell's frame) and the
 // first NS slots of one staged cell; unused slots hold the sentinel
 template <int NS, int PLC>
-__device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float npy)
+__device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float npy, float macc)
 {
     const float4 p0 = *reinterpret_cast<const float4 *>(cp), p1 = *reinterpret_cast<const float4 *>(cp + PLC * 16);
     // sign bit of y3 = "this cell holds 5 or more disks" (cell-local coordinates are positive):
@@ -145,16 +145,18 @@ __device__ __forceinline__ float cell_min_d2(const char *cp, float npx, float np
     const float2 nx = make_float2(npx, npx), ny = make_float2(npy, npy);
     const float2 a = pair2(p0.x, p0.y, p1.x, p1.y, nx, ny);
     const float2 b = pair2(p0.z, p0.w, p1.z, fabsf(p1.w), nx, ny);
-    float m = fminf(fminf(a.x, a.y), fminf(b.x, b.y));
+    // running minimum `macc` threaded through, every step a 3-input min (FMNMX3): two new values per instruction
+    float m = fminf(fminf(a.x, a.y), b.x);
+    m = fminf(fminf(m, b.y), macc);
     if (NS >= 6) {
         if (more) {
             const float4 p2 = *reinterpret_cast<const float4 *>(cp + 2 * PLC * 16);
             const float2 c = pair2(p2.x, p2.y, p2.z, p2.w, nx, ny);
-            m = fminf(m, fminf(c.x, c.y));
+            m = fminf(fminf(m, c.x), c.y);
             if (NS == 8) {
                 const float4 p3 = *reinterpret_cast<const float4 *>(cp + 3 * PLC * 16);
                 const float2 e = pair2(p3.x, p3.y, p3.z, p3.w, nx, ny);
-                m = fminf(m, fminf(e.x, e.y));
+                m = fminf(fminf(m, e.x), e.y);
             }
         }
     }
@@ -323,10 +325,9 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const float npys = -__fadd_rn(py, goD ? w : -w);
         const char *cH = cL + (goL ? 0 : 16);
         const int dV = goD ? -PITCH * 16 : PITCH * 16;
-        float m = cell_min_d2<NS, PLC>(cH, npxs, -py);
-        m = fminf(m, cell_min_d2<NS, PLC>(cown + dV, -px, npys));
-        m = fminf(m, cell_min_d2<NS, PLC>(cH + dV, npxs, npys));
-        return m;
+        float m = cell_min_d2<NS, PLC>(cH, npxs, -py, 3.0e38f);
+        m = cell_min_d2<NS, PLC>(cown + dV, -px, npys, m);
+        return cell_min_d2<NS, PLC>(cH + dV, npxs, npys, m);
     };
 
     float ox[8] = { p0.x, p0.y, p0.z, p0.w, p2.x, p2.y, p3.x, p3.y };
@@ -365,23 +366,25 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
         const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
         float2 d01 = pair2(ox[0], ox[1], oy[0], oy[1], npx, npy);
         float2 d23 = pair2(ox[2], ox[3], oy[2], oy[3], npx, npy);
-        const float big = 3.0e38f;
-        if (s == 0) d01.x = big;
-        if (s == 1) { d01.y = cA ? big : d01.y; d01.x = cA ? d01.x : big; }
-        if (s == 2) { d23.x = cA ? big : d23.x; d01.x = cA ? d01.x : big; }
-        if (s == 3) { d23.y = cA ? big : d23.y; d01.y = cB ? big : d01.y; d01.x = (cA | cB) ? d01.x : big; }
-        m = fminf(m, fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)));
+        // j != slot: of slots 0..3 the moved one is left out (one select per pair it can be in, not one per slot)
+        if (s == 0) m = fminf(fminf(m, d01.y), fminf(d23.x, d23.y));
+        if (s == 1) m = fminf(fminf(m, cA ? d01.x : d01.y), fminf(d23.x, d23.y));                       // slot 1, or 0 (cnt == 1)
+        if (s == 2) m = fminf(fminf(m, cA ? d01.x : d23.x), fminf(d01.y, d23.y));                       // slot 2, or 0 (cnt <= 2)
+        if (s == 3) {                                                                                   // slot 3, 1 (cnt == 2) or 0 (cnt == 1, 3)
+            const float u = (cA | cB) ? d01.x : d01.y, v = cA ? d01.y : d23.y;
+            m = fminf(fminf(m, u), fminf(v, d23.x));
+        }
         if (NS >= 6) {
             const float2 d45 = pair2(ox[4], ox[5], oy[4], oy[5], npx, npy);
-            m = fminf(m, fminf(d45.x, d45.y));
+            m = fminf(fminf(m, d45.x), d45.y);
         }
         if (NS == 8) {
             const float2 d67 = pair2(ox[6], ox[7], oy[6], oy[7], npx, npy);
-            m = fminf(m, fminf(d67.x, d67.y));
+            m = fminf(fminf(m, d67.x), d67.y);
         }
         // accept_move subsweep.h:194-217 (hard disks: accept iff in bounds and no overlap)
         const bool acc = inb && !(m < sigma2);      // out of the cell: rejected whatever the neighbours say
-        n_acc += acc ? 1u : 0u;
+        if (acc) n_acc += 1u;
         if (s == 0) { ox[0] = acc ? px : ox[0]; oy[0] = acc ? py : oy[0]; }
         else {
             const bool w0 = acc & !cA & !cB, w1 = acc & cB, ws = acc & cA;
