@@ -674,6 +674,7 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         a.dbg_skip = dbg;
         a.prefetch_ahead = pf_ahead;
         pmc4_plan_sweep(a, dbg & 64);               // tile extent and halo from the colour order (64: always the full halo)
+        pmc4_philox_prepare(a, h->g4);
         if (ty_cap && a.ty > ty_cap) a.ty = ty_cap; // small systems: shorter tiles, more CTAs per sweep
         h->v4_epoch[cur ^ 1] = next_epoch();
         a.flag_in = h->v4_flags[cur]; a.epoch_in = h->v4_epoch[cur];

@@ -334,12 +334,13 @@ __device__ __forceinline__ void colour_pass(float4 *sm, const TileCtx &t, const 
     float oy[8] = { p1.x, p1.y, p1.z, fabsf(p1.w), p2.z, p2.w, p3.z, p3.w };     // y3 carries the "5 or more" flag in its sign
     // ONE Philox call per cell and sub-sweep: word s feeds trial s (shuffle: bits 24-31, dx: bits 12-23, dy: bits 0-11)
     uint32_t rw[4];
-    philox4x32_10_keys(cell_id, a.sweep_lo, a.sweep_hi, 0u, g.pk0, g.pk1, rw[0], rw[1], rw[2], rw[3]);
+    philox_cell(cell_id, a.ph_e1, a.ph_e2, a.ph_e3, g.pk0, g.pk1, rw[0], rw[1], rw[2], rw[3]);
     // random_shuffle subsweep.h:50-58: physical partial Fisher-Yates, steps 0..3
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-        // jd = jj - s = ((r >> 24) * (cnt - s)) >> 8 as the high half of one product; s >= cnt: 0 remaining slots, jd = 0 (no-op)
-        const int jd = (int)__umulhi(rw[s] & 0xFF000000u, (uint32_t)max(cnt - s, 0));
+        // jd = jj - s = ((r >> 24) * (cnt - s)) >> 8 as the high half of one product.  s >= cnt (no slot left): cnt - s
+        // wraps to 2^32 - k, the product's high half is 0 (top byte 0) or >= 2^24 - 1: never one of the 1 .. 5 tested below
+        const int jd = (int)__umulhi(rw[s] & 0xFF000000u, (uint32_t)(cnt - s));
         const float tx = ox[s], ty = oy[s];
         float nx = tx, ny = ty;
 #pragma unroll
@@ -987,6 +988,18 @@ void pmc4_plan_sweep(SweepArgs &a, int full_halo)
     a.sh_nseg = kNT / a.tx;
     a.sh_inv = 65536 / a.tx + 1;
     a.sh_inv2 = 65536 / a.sh_nseg + 1;
+}
+
+// The sweep-only part of the cells' Philox calls (philox_cell): counter = {cell, sweep_lo, sweep_hi, 0}.
+void pmc4_philox_prepare(SweepArgs &a, const Geom4 &g)
+{
+    const unsigned long long p1 = 0xCD9E8D57ull * a.sweep_hi;                   // round 0, the product of counter word 2
+    const unsigned a0 = (unsigned)(p1 >> 32) ^ a.sweep_lo ^ g.pk0[0];           // -> counter word 0 of round 1
+    const unsigned a1 = (unsigned)p1;                                           // -> counter word 1 of round 1
+    const unsigned long long q0 = 0xD2511F53ull * a0;                           // round 1, the product of counter word 0
+    a.ph_e1 = a1 ^ g.pk0[1];
+    a.ph_e2 = (unsigned)(q0 >> 32) ^ g.pk1[1];
+    a.ph_e3 = (unsigned)q0 ^ g.pk1[2];
 }
 
 int pmc4_tile_rows(const Geom4 &g, const SweepArgs &a) { return (g.rows + a.ty - 1) / a.ty; }
