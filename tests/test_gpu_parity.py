@@ -291,9 +291,9 @@ def test_run_host_non_blocking_on_two_handles_matches_the_oracle():
     odisk, on = o.assign(r)
     o.sweep(odisk, on, 0, 6)
     rh = torch.from_numpy(r).pin_memory()
-    hs, outs = [], []
-    for _ in range(2):
-        with torch.cuda.stream(torch.cuda.Stream()):
+    hs, outs, streams = [], [], [torch.cuda.Stream(), torch.cuda.Stream()]     # the handles borrow the streams: keep them alive
+    for st in streams:
+        with torch.cuda.stream(st):
             mc = pmc_b200.ParallelMC(N, **kw)
         mc.set_blocking(0)
         g = mc.geom
