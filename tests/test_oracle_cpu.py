@@ -28,6 +28,35 @@ def test_philox_kat(ctr, key, expect):
     assert O.philox(ctr, key) == expect
 
 
+def test_philox_sweep_constants_give_the_same_words():
+    """The fused kernel computes, once per sweep on the host (pmc4_philox_prepare), what rounds 0-2 of a cell's
+    Philox call owe to (seed, sweep) alone - only counter word 0 (the cell id) differs between the cells of a sweep -
+    and folds it into three constants e1, e2, e3 (philox_cell, pmc_internal.cuh).  The same algebra in Python against
+    the KAT-pinned oracle Philox: identical words for random seeds, sweeps and cells."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        seed_lo, seed_hi, sw_lo, sw_hi, cell = (int(v) for v in rng.integers(0, 2 ** 32, 5, dtype=np.uint64))
+        k0 = [(seed_lo + r * W0) & MASK for r in range(10)]
+        k1 = [(seed_hi + r * W1) & MASK for r in range(10)]
+        # host, once per sweep
+        p1 = M1 * sw_hi
+        a0, a1 = (p1 >> 32) ^ sw_lo ^ k0[0], p1 & MASK
+        q0 = M0 * a0
+        e1, e2, e3 = a1 ^ k0[1], (q0 >> 32) ^ k1[1], (q0 & MASK) ^ k1[2]
+        # device, per cell
+        p0 = M0 * cell
+        c2, c3 = (p0 >> 32) ^ k1[0], p0 & MASK                       # round 0
+        p1 = M1 * c2
+        c0, c1, c2 = (p1 >> 32) ^ e1, p1 & MASK, c3 ^ e2            # round 1
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0[2], p1 & MASK, (p0 >> 32) ^ e3, p0 & MASK     # round 2
+        for r in range(3, 10):
+            p0, p1 = M0 * c0, M1 * c2
+            c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0[r], p1 & MASK, (p0 >> 32) ^ c3 ^ k1[r], p0 & MASK
+        assert (c0, c1, c2, c3) == tuple(O.philox((cell, sw_lo, sw_hi, 0), (seed_lo, seed_hi)))
+
+
 # ---------------------------------------------------------------- geometry (SURVEY section 8 table)
 @pytest.mark.parametrize("N,phi,cps,mult", [
     (4096, 0.70, 32, 2), (2 ** 20, 0.70, 542, 2), (2 ** 24, 0.716, 2144, 2),
