@@ -126,7 +126,7 @@ int  pmc_set_stream(pmc_handle *h, void *cuda_stream);   /* default: a handle-ow
 int  pmc_set_blocking(pmc_handle *h, int blocking);      /* default 1 (start.cu syncs after every launch) */
 int  pmc_synchronize(pmc_handle *h);
 /* Knobs that choose WHICH kernel / schedule computes the result, never the result itself (bit-identical for
- * every setting; tests use them to drive the rare paths): "bands" 1..8, "prefetch" >= 0, "overlap" 0/1,
+ * every setting; tests use them to drive the rare paths): "bands" 1..16, "prefetch" >= 0, "overlap" 0/1,
  * "generic" 0/1, "four_plane" 0/1, "force_crowded" 0/1, "no_ns4" 0/1, "full_halo" 0/1, "tile_rows" 0 (automatic)
  * or an even number 2..28.  Unknown name: PMC_E_INVALID.
  * The library reads no environment variable that can change a result. */

@@ -57,7 +57,7 @@ static bool nccl_load()
 }
 
 // ------------------------------------------------------------------ handle
-constexpr int kMaxBands = 8;
+constexpr int kMaxBands = 16;
 constexpr int kGhostRows = 5;   // fused sweep halo (4) + 1 upstream row of the pending shift
 constexpr int kFlagRows = 3;    // rows of 2 x 2 flag blocks that cover kMY = 5 rows starting at an odd or even row
 
@@ -614,11 +614,6 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
         }
     }
     const int pf_ahead = h->tune_prefetch;
-    // tile height: what the colour order allows (24..28 rows) unless the whole system is less than ~1.5 waves of such
-    // tiles (148 SMs x 4 CTAs): then 16-row tiles, whose shorter CTAs shorten the dependency chain from sweep to sweep
-    // (N = 2^20: 28.9 -> 25.9 us per sweep; larger systems lose throughput to the deeper halo).  "tile_rows" overrides.
-    int ty_cap = h->tune_tile_rows;
-    if (!ty_cap && (long long)((h->g4.cps + 27) / 28) * ((h->g4.rows + 25) / 26) < 888) ty_cap = 16;
     // the event pair that times the sweep kernels of this call; owned by this scope until it is queued
     struct EvPair {
         cudaEvent_t a = nullptr, b = nullptr;
@@ -633,16 +628,22 @@ static int sweep_v4(pmc_handle *h, float *d_disk, int16_t *d_n, uint64_t sweep0,
     // sweep t+1 reads and overwrites only what bands b-1, b, b+1 (periodic) of sweep t wrote and read, so it
     // waits for those three alone: the last CTAs of sweep t and the first of t+1 share the GPU, there is no
     // idle tail and no launch gap between sweeps.
+    // tile height: what the colour order allows (24..29 rows) unless the whole system is less than ~1.5 waves of such
+    // tiles (148 SMs x 4 CTAs): then 16-row tiles, whose shorter CTAs shorten the dependency chain from sweep to sweep
+    // (N = 2^20: 28.9 -> 25.9 us per sweep; larger systems lose throughput to the deeper halo).  "tile_rows" overrides.
+    int ty_cap = h->tune_tile_rows;
+    if (!ty_cap && (long long)((h->g4.cps + 27) / 28) * ((h->g4.rows + 25) / 26) < 888) ty_cap = 16;
+    const int ty_max = ty_cap ? (ty_cap < 29 ? ty_cap : 29) : 29;    // tallest tile any sweep of this call can plan
     const int bands_env = h->tune_bands;
-    // at least 3 tile rows per band whatever this call's sweeps choose as tile height (<= 28 rows), at least
+    // at least 3 tile rows per band whatever this call's sweeps choose as tile height (<= ty_max rows), at least
     // 4 bands (with 3, every band is every other band's neighbour); fixed for the whole call
-    int bands = (h->g4.rows + 27) / 28 / 3;
+    int bands = (h->g4.rows + ty_max - 1) / ty_max / 3;
     if (bands > bands_env) bands = bands_env;
     if (bands > kMaxBands) bands = kMaxBands;
     if (bands < 4 || h->p.n_ranks != 1 || n_sweeps < 2) bands = 1;
     // slabs: the interior tile rows (all but one tile row per face) in bands likewise; only the two outer
     // bands depend on the boundary rows and their exchange
-    int sbands = ((h->g4.rows + 27) / 28 - 4) / 3;      // 3 * sbands <= (rows - 5) / 28 - 1 <= interior tile rows of any sweep
+    int sbands = ((h->g4.rows + ty_max - 1) / ty_max - 4) / 3;      // 3 * sbands <= (rows - 5) / ty_max - 1 <= interior tile rows of any sweep
     if (sbands > bands_env) sbands = bands_env;
     if (sbands > kMaxBands) sbands = kMaxBands;
     if (sbands < 3 || h->p.n_ranks == 1 || !overlap || n_sweeps < 2) sbands = 1;
